@@ -1,0 +1,740 @@
+// The three kernels of one batched cost+gradient evaluation (SE3GCOPTER::objectiveFunc,
+// se3gcopter_cpu.hpp "CPU.hpp" :961-1000), hand-written for sm_100a, fp64 throughout:
+//
+//   K1 minco_forward_kernel   x=(tau,xi) -> T, q -> banded MINCO system -> LU -> c      (one warp / trajectory)
+//        forwardT CPU.hpp:626, splitToFineT :930, forwardP :729, MINCO_S3::generate :425,
+//        BandedSystem::factorizeLU/solve trajectory.hpp:655/692
+//   K2 penalty_kernel         c -> per-piece penalty integral, dJ/dc, dJ/dT, jerk energy  (samples x pieces x batch)
+//        MINCO_S3::addTimeIntPenalty CPU.hpp:188-408, getTrajJerkCost :507, addGradJbyT :65, addGradJbyC :80
+//   K3 minco_backward_kernel  dJ/dc -> adjoint solve -> dJ/dT, dJ/dq -> dJ/d(tau,xi), cost (one warp / trajectory)
+//        BandedSystem::solveAdj trajectory.hpp:724, addPropCtoT CPU.hpp:104, addPropCtoP :154,
+//        mergeToCoarseGradT :946, addLayerTGrad :816, addLayerPGrad :897, rho terms :988-989
+//
+// No tensor cores: the largest contraction on this path is 6x3 . 3x3.  See DESIGN.md for the
+// roofline of each kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "device_batch.cuh"
+
+namespace frx {
+
+// ------------------------------------------------------------------------------------------------
+// Band storage used on the device: row-major, 16 doubles per row: slot (j - i + 6) for column j of
+// row i (13 diagonals, bandwidth 6/6 as trajectory.hpp:645 with N-major order swapped for coalesced
+// row access), slots 13..15 = the three right-hand sides (x,y,z).
+// ------------------------------------------------------------------------------------------------
+#define BW 16
+
+__device__ __forceinline__ double c2_forward(double t) {  // CPU.hpp:639-641
+    return t > 0.0 ? ((0.5 * t + 1.0) * t + 1.0) : 1.0 / ((0.5 * t - 1.0) * t + 1.0);
+}
+
+// K1 ---------------------------------------------------------------------------------------------
+// smem: As[N][16] | cs[N][3] | Tc[coarseN]
+__global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (bv.active && !bv.active[b]) return;
+    const int lane = threadIdx.x;
+    const int p0 = bv.piece_off[b];
+    const int M = bv.piece_off[b + 1] - p0;
+    const int N = 6 * M;
+    const int co0 = bv.coarse_off[b];
+    const int coarseN = bv.coarse_off[b + 1] - co0;
+    const DevParams par = bv.par[b];
+    const double* x = xin + bv.x_off[b];
+    const int dimT = bv.dimT[b];
+    double* As = sm;
+    double* cs = As + (size_t)N * BW;
+    double* Tc = cs + (size_t)N * 3;
+
+    // ---- forwardT (CPU.hpp:626-676) ----
+    if (par.softT) {
+        for (int i = lane; i < coarseN; i += 32) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+    } else {
+        if (lane == 0) {  // fixed total time: sequential sums as in the reference (rare path)
+            const int Ms1 = dimT;
+            for (int i = 0; i < Ms1; i++) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+            Tc[Ms1] = 0.0;
+            double s = 0.0;
+            for (int i = 0; i <= Ms1; i++) s += Tc[i];
+            const double den = 1.0 + s;
+            for (int i = 0; i <= Ms1; i++) Tc[i] /= den;
+            s = 0.0;
+            for (int i = 0; i <= Ms1; i++) s += Tc[i];
+            Tc[Ms1] = 1.0 - s;
+            for (int i = 0; i <= Ms1; i++) Tc[i] *= par.sumT;
+        }
+    }
+    for (int i = lane; i < N * BW; i += 32) As[i] = 0.0;
+    __syncwarp();
+    // ---- splitToFineT (CPU.hpp:930-944) + forwardP (CPU.hpp:729-747) ----
+    for (int i = lane; i < M; i += 32) {
+        const int pl = bv.piece_poly[p0 + i];
+        const double Ti = Tc[pl] / bv.intervals[co0 + pl];
+        bv.T[p0 + i] = Ti;
+        if (i < M - 1) {
+            const int k = bv.wp_vert_cnt[p0 + i] - 1;
+            const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
+            const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
+            double sn = 0.0;
+            for (int a = 0; a < k; a++) sn += xi[a] * xi[a];
+            const double sc = 2.0 / (1.0 + sn);
+            double qx = 0.0, qy = 0.0, qz = 0.0;
+            for (int a = 0; a < k; a++) {
+                const double r = sc * xi[a];
+                const double rr = r * r;
+                qx += V[3 * (a + 1) + 0] * rr;
+                qy += V[3 * (a + 1) + 1] * rr;
+                qz += V[3 * (a + 1) + 2] * rr;
+            }
+            qx += V[0], qy += V[1], qz += V[2];
+            bv.q[3 * (size_t)(p0 + i) + 0] = qx;
+            bv.q[3 * (size_t)(p0 + i) + 1] = qy;
+            bv.q[3 * (size_t)(p0 + i) + 2] = qz;
+            // junction rows 6i+3 .. 6i+8 of A and the waypoint RHS (CPU.hpp:446-478)
+            const double T1 = Ti, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+            const int r = 6 * i;
+#define A_(row, col) As[(size_t)(row) * BW + ((col) - (row) + 6)]
+            A_(r + 3, r + 3) = 6.0;
+            A_(r + 3, r + 4) = 24.0 * T1;
+            A_(r + 3, r + 5) = 60.0 * T2;
+            A_(r + 3, r + 9) = -6.0;
+            A_(r + 4, r + 4) = 24.0;
+            A_(r + 4, r + 5) = 120.0 * T1;
+            A_(r + 4, r + 10) = -24.0;
+            A_(r + 5, r) = 1.0;
+            A_(r + 5, r + 1) = T1;
+            A_(r + 5, r + 2) = T2;
+            A_(r + 5, r + 3) = T3;
+            A_(r + 5, r + 4) = T4;
+            A_(r + 5, r + 5) = T5;
+            A_(r + 6, r) = 1.0;
+            A_(r + 6, r + 1) = T1;
+            A_(r + 6, r + 2) = T2;
+            A_(r + 6, r + 3) = T3;
+            A_(r + 6, r + 4) = T4;
+            A_(r + 6, r + 5) = T5;
+            A_(r + 6, r + 6) = -1.0;
+            A_(r + 7, r + 1) = 1.0;
+            A_(r + 7, r + 2) = 2 * T1;
+            A_(r + 7, r + 3) = 3 * T2;
+            A_(r + 7, r + 4) = 4 * T3;
+            A_(r + 7, r + 5) = 5 * T4;
+            A_(r + 7, r + 7) = -1.0;
+            A_(r + 8, r + 2) = 2.0;
+            A_(r + 8, r + 3) = 6 * T1;
+            A_(r + 8, r + 4) = 12 * T2;
+            A_(r + 8, r + 5) = 20 * T3;
+            A_(r + 8, r + 8) = -2.0;
+            As[(size_t)(r + 5) * BW + 13] = qx;
+            As[(size_t)(r + 5) * BW + 14] = qy;
+            As[(size_t)(r + 5) * BW + 15] = qz;
+        } else {
+            // last piece: tail rows (CPU.hpp:481-499) and, by the same lane, the head rows (:437-442)
+            const double T1 = Ti, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+            const int e = N;
+            A_(e - 3, e - 6) = 1.0;
+            A_(e - 3, e - 5) = T1;
+            A_(e - 3, e - 4) = T2;
+            A_(e - 3, e - 3) = T3;
+            A_(e - 3, e - 2) = T4;
+            A_(e - 3, e - 1) = T5;
+            A_(e - 2, e - 5) = 1.0;
+            A_(e - 2, e - 4) = 2 * T1;
+            A_(e - 2, e - 3) = 3 * T2;
+            A_(e - 2, e - 2) = 4 * T3;
+            A_(e - 2, e - 1) = 5 * T4;
+            A_(e - 1, e - 4) = 2;
+            A_(e - 1, e - 3) = 6 * T1;
+            A_(e - 1, e - 2) = 12 * T2;
+            A_(e - 1, e - 1) = 20 * T3;
+            A_(0, 0) = 1.0;
+            A_(1, 1) = 1.0;
+            A_(2, 2) = 2.0;
+            const double* ht = bv.headtail + 18 * (size_t)b;
+            for (int d = 0; d < 3; d++) {
+                As[0 * BW + 13 + d] = ht[0 + d];
+                As[1 * BW + 13 + d] = ht[3 + d];
+                As[2 * BW + 13 + d] = ht[6 + d];
+                As[(size_t)(e - 3) * BW + 13 + d] = ht[9 + 0 + d];
+                As[(size_t)(e - 2) * BW + 13 + d] = ht[9 + 3 + d];
+                As[(size_t)(e - 1) * BW + 13 + d] = ht[9 + 6 + d];
+            }
+#undef A_
+        }
+    }
+    __syncwarp();
+
+    // ---- banded LU without pivoting (trajectory.hpp:655-687) fused with the forward substitution
+    //      of the three right-hand sides (:695-705).  Pivot k: the 6 rows below x (6 columns + 3 RHS)
+    //      = 54 updates, spread as 6 row groups x 5 lanes, <= 2 slots per lane.  The reference's
+    //      skip-exact-zero tests only skip arithmetic that leaves the data unchanged.
+    {
+        const int r = lane / 5, cg = lane - 5 * r;
+        const bool act = lane < 30;
+        for (int k = 0; k <= N - 2; k++) {
+            const int i = k + 1 + r;
+            const bool on = act && i < N;
+            double l = 0.0, v0 = 0.0, v1 = 0.0;
+            if (on) {
+                l = As[(size_t)i * BW + (5 - r)] / As[(size_t)k * BW + 6];
+                // slot s: s<6 -> matrix column k+1+s ; s>=6 -> RHS s-6
+                const int s0 = cg, s1 = cg + 5;
+                const int src0 = (s0 < 6) ? (7 + s0) : (13 + s0 - 6);
+                const int dst0 = (s0 < 6) ? (6 + s0 - r) : (13 + s0 - 6);
+                v0 = As[(size_t)i * BW + dst0] - l * As[(size_t)k * BW + src0];
+                if (s1 < 9) {
+                    const int src1 = (s1 < 6) ? (7 + s1) : (13 + s1 - 6);
+                    const int dst1 = (s1 < 6) ? (6 + s1 - r) : (13 + s1 - 6);
+                    v1 = As[(size_t)i * BW + dst1] - l * As[(size_t)k * BW + src1];
+                }
+            }
+            __syncwarp();
+            if (on) {
+                const int s0 = cg, s1 = cg + 5;
+                const int dst0 = (s0 < 6) ? (6 + s0 - r) : (13 + s0 - 6);
+                As[(size_t)i * BW + dst0] = v0;
+                if (s1 < 9) {
+                    const int dst1 = (s1 < 6) ? (6 + s1 - r) : (13 + s1 - 6);
+                    As[(size_t)i * BW + dst1] = v1;
+                }
+                if (cg == 0) As[(size_t)i * BW + (5 - r)] = l;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- back substitution (trajectory.hpp:706-717): 6 rows above x 3 RHS = 18 lanes ----
+    {
+        const int r = lane / 3, d = lane - 3 * r;
+        const bool act = lane < 18;
+        for (int j = N - 1; j >= 0; j--) {
+            if (act) {
+                const double xj = As[(size_t)j * BW + 13 + d] / As[(size_t)j * BW + 6];
+                const int i = j - 1 - r;
+                if (i >= 0) As[(size_t)i * BW + 13 + d] -= As[(size_t)i * BW + (7 + r)] * xj;
+                if (r == 0) cs[3 * j + d] = xj;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- write c (6M x 3 row-major == per-piece 6x3 blocks) and the LU factors ----
+    double* cg_ = bv.c + 18 * (size_t)p0;
+    for (int i = lane; i < 3 * N; i += 32) cg_[i] = cs[i];
+    double* lug = bv.lu + (size_t)BW * 6 * p0;
+    for (int i = lane; i < N * BW; i += 32) lug[i] = As[i];
+}
+
+// K2 ---------------------------------------------------------------------------------------------
+// normalizeFDF (CPU.hpp:163-185): x/|x| and the symmetric Jacobian (|x|^2 I - x x^T)/|x|^3.
+struct Sym3 {
+    double xx, yy, zz, xy, xz, yz;
+};
+__device__ __forceinline__ Sym3 unit_jacobian(double a, double b, double c, double sq, double nrm) {
+    const double den = sq * nrm;
+    Sym3 G;
+    G.xx = (b * b + c * c) / den;
+    G.yy = (a * a + c * c) / den;
+    G.zz = (a * a + b * b) / den;
+    G.xy = -(a * b) / den;
+    G.xz = -(c * a) / den;
+    G.yz = -(b * c) / den;
+    return G;
+}
+
+// smem: cblk[ppc][18] | fc[ppc][6*max_faces] | part[ppc*tpp][20]
+__global__ void __launch_bounds__(256) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int gp_base = blockIdx.x * pl.ppc;
+    const int npieces = min(pl.ppc, bv.total_pieces - gp_base);
+    double* cblk = sm;
+    double* fc = cblk + (size_t)pl.ppc * 18;
+    double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
+
+    // ---- stage the 6x3 coefficient blocks and the face lists of this CTA's pieces ----
+    for (int i = tid; i < npieces * 18; i += blockDim.x) cblk[i] = bv.c[18 * (size_t)gp_base + i];
+    for (int p = 0; p < npieces; p++) {
+        const int gp = gp_base + p;
+        const int nf = bv.piece_face_cnt[gp] * 6;
+        const double* src = bv.faces + 6 * (size_t)bv.piece_face_off[gp];
+        double* dst = fc + (size_t)p * 6 * bv.max_faces;
+        for (int i = tid; i < nf; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int pl_piece = tid / pl.tpp;
+    const int chunk = tid - pl_piece * pl.tpp;
+    double acc[20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) acc[i] = 0.0;
+
+    if (pl_piece < npieces && !(bv.active && !bv.active[bv.piece_traj[gp_base + pl_piece]])) {
+        const int gp = gp_base + pl_piece;
+        const DevParams& P = bv.par[bv.piece_traj[gp]];
+        const double* c = cblk + pl_piece * 18;
+        const double* faces = fc + (size_t)pl_piece * 6 * bv.max_faces;
+        const int F = bv.piece_face_cnt[gp];
+        const int K = bv.cons[gp];
+        const int S = K + 1;
+        const double Ti = bv.T[gp];
+        const double step = Ti / K;
+        const double invK = 1.0 / K;
+        const int j0 = chunk * pl.spt;
+        const int j1 = min(j0 + pl.spt, S);
+        // running-sum abscissa exactly as the reference: s1 = 0; s1 += step (CPU.hpp:246,400)
+        double s1 = 0.0;
+        for (int j = 0; j < j0 && j < S; j++) s1 += step;
+        const double ex = P.ell[0], ey = P.ell[1], ez = P.ell[2];
+
+        for (int j = j0; j < j1; j++) {
+            const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+            const double alpha = invK * j;
+            const double omg = (j == 0 || j == S - 1) ? 0.5 : 1.0;
+            const double w = omg * step;
+            double pos[3], vel[3], ac[3], jer[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double c0 = c[d], c1 = c[3 + d], c2 = c[6 + d], c3 = c[9 + d], c4 = c[12 + d], c5 = c[15 + d];
+                pos[d] = c0 + c1 * s1 + c2 * s2 + c3 * s3 + c4 * s4 + c5 * s5;
+                vel[d] = c1 + c2 * (2.0 * s1) + c3 * (3.0 * s2) + c4 * (4.0 * s3) + c5 * (5.0 * s4);
+                ac[d] = c2 * 2.0 + c3 * (6.0 * s1) + c4 * (12.0 * s2) + c5 * (20.0 * s3);
+                jer[d] = c3 * 6.0 + c4 * (24.0 * s1) + c5 * (60.0 * s2);
+            }
+            // body frame (CPU.hpp:266-279)
+            const double hx = ac[0], hy = ac[1], hz = ac[2] + P.gacc;
+            const double hsq = hx * hx + hy * hy + hz * hz;
+            const double fThr = sqrt(hsq);
+            const double zx = hx / fThr, zy = hy / fThr, zz = hz / fThr;
+            // czB = (0, zz, -zy)
+            const double csq = zz * zz + zy * zy;
+            const double cn = sqrt(csq);
+            const double yx = 0.0, yy = zz / cn, yz = -zy / cn;
+            // xB = yB x zB
+            const double xx = yy * zz - yz * zy, xy = yz * zx - yx * zz, xz = yx * zy - yy * zx;
+
+            // adjoint 3-vectors of pos / vel / acc / jer for this sample, plus the pieces that do
+            // not go through them
+            double g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, g3[3] = {0, 0, 0};
+            double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef*e_m*n  (m = x,y,z body axis)
+            double cst = 0.0, direct = 0.0;
+            bool sfc_on = false;
+
+            // ---- safe-flight-corridor faces (CPU.hpp:310-345) ----
+            if (P.chi[0] != 0.0) {  // chi0 == 0 adds exact zeros in the reference
+                for (int k = 0; k < F; k++) {
+                    const double nx = faces[6 * k], ny = faces[6 * k + 1], nz = faces[6 * k + 2];
+                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
+                    const double uy = (yx * nx + yy * ny + yz * nz) * ey;
+                    const double uz = (zx * nx + zy * ny + zz * nz) * ez;
+                    const double eNorm = sqrt(ux * ux + uy * uy + uz * uz);
+                    const double sd = nx * (pos[0] - faces[6 * k + 3]) + ny * (pos[1] - faces[6 * k + 4]) +
+                                      nz * (pos[2] - faces[6 * k + 5]) + eNorm + P.margin;
+                    if (sd > 0.0) {
+                        const double sd2 = sd * sd, sd3 = sd * sd2;
+                        const double coef = w * P.chi[0] * 3.0 * sd2;
+                        const double e0 = ux / eNorm * ex, e1 = uy / eNorm * ey, e2 = uz / eNorm * ez;
+                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
+                        ax[0] += coef * e0 * nx, ax[1] += coef * e0 * ny, ax[2] += coef * e0 * nz;
+                        ay[0] += coef * e1 * nx, ay[1] += coef * e1 * ny, ay[2] += coef * e1 * nz;
+                        az[0] += coef * e2 * nx, az[1] += coef * e2 * ny, az[2] += coef * e2 * nz;
+                        cst += w * P.chi[0] * sd3;
+                        direct += omg * P.chi[0] * sd3 * invK;
+                        sfc_on = true;
+                    }
+                }
+            }
+            // ---- velocity (CPU.hpp:347-359) ----
+            const double violaVel = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - P.vmax_sqr;
+            if (violaVel > 0.0) {
+                const double v2 = violaVel * violaVel, v3 = v2 * violaVel;
+                const double coef = w * P.chi[1] * (3.0 * v2) * 2.0;
+                g1[0] += coef * vel[0], g1[1] += coef * vel[1], g1[2] += coef * vel[2];
+                cst += w * P.chi[1] * v3;
+                direct += omg * P.chi[1] * v3 * invK;
+            }
+            // ---- thrust (CPU.hpp:361-385) ----
+            const double sqrMagThr = fThr * fThr;
+            const double violaThrl = P.thrmin_sqr - sqrMagThr;
+            const double violaThrh = sqrMagThr - P.thrmax_sqr;
+            if (violaThrl > 0.0) {
+                const double v2 = violaThrl * violaThrl, v3 = v2 * violaThrl;
+                const double coef = -(w * P.chi[2] * (3.0 * v2) * 2.0);
+                g2[0] += coef * hx, g2[1] += coef * hy, g2[2] += coef * hz;
+                cst += w * P.chi[2] * v3;
+                direct += omg * P.chi[2] * v3 * invK;
+            }
+            if (violaThrh > 0.0) {
+                const double v2 = violaThrh * violaThrh, v3 = v2 * violaThrh;
+                const double coef = w * P.chi[2] * (3.0 * v2) * 2.0;
+                g2[0] += coef * hx, g2[1] += coef * hy, g2[2] += coef * hz;
+                cst += w * P.chi[2] * v3;
+                direct += omg * P.chi[2] * v3 * invK;
+            }
+            // ---- body rate (CPU.hpp:285-304, 387-398) ----
+            const double r0 = xx * jer[0] + xy * jer[1] + xz * jer[2];
+            const double r1 = yx * jer[0] + yy * jer[1] + yz * jer[2];
+            const double r2 = zx * jer[0] + zy * jer[1] + zz * jer[2];
+            const double bd0 = r0 / fThr, bd1 = r1 / fThr;
+            const double violaBdr = bd1 * bd1 + bd0 * bd0 - P.bdrmax_sqr;
+            const bool bdr_on = violaBdr > 0.0;
+
+            if (sfc_on || bdr_on) {
+                // Jacobians of the frame w.r.t. acc (CPU.hpp:268-278): dzB symmetric; dyB = dn * cdzB;
+                // dxB[:,m] = dyB[:,m] x zB + yB x dzB[:,m]
+                const Sym3 Z = unit_jacobian(hx, hy, hz, hsq, fThr);
+                const Sym3 Cn = unit_jacobian(0.0, zz, -zy, csq, cn);
+                // cdzB rows: 0 ; dzB.row(2) ; -dzB.row(1)
+                const double cd1[3] = {Z.xz, Z.yz, Z.zz};
+                const double cd2[3] = {-Z.xy, -Z.yy, -Z.yz};
+                double dY[3][3], dX[3][3];
+                const double dZ[3][3] = {{Z.xx, Z.xy, Z.xz}, {Z.xy, Z.yy, Z.yz}, {Z.xz, Z.yz, Z.zz}};
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    dY[0][m] = Cn.xy * cd1[m] + Cn.xz * cd2[m];
+                    dY[1][m] = Cn.yy * cd1[m] + Cn.yz * cd2[m];
+                    dY[2][m] = Cn.yz * cd1[m] + Cn.zz * cd2[m];
+                }
+#pragma unroll
+                for (int m = 0; m < 3; m++) {
+                    // dyB.col(m) x zB + yB x dzB.col(m)
+                    dX[0][m] = (dY[1][m] * zz - dY[2][m] * zy) + (yy * dZ[2][m] - yz * dZ[1][m]);
+                    dX[1][m] = (dY[2][m] * zx - dY[0][m] * zz) + (yz * dZ[0][m] - yx * dZ[2][m]);
+                    dX[2][m] = (dY[0][m] * zy - dY[1][m] * zx) + (yx * dZ[1][m] - yy * dZ[0][m]);
+                }
+                if (sfc_on) {
+                    // g2 += sum_m dB_m^T a_m  (w of SURVEY A.4 summed over active faces)
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
+                        g2[cc] += (dX[0][cc] * ax[0] + dX[1][cc] * ax[1] + dX[2][cc] * ax[2]) +
+                                  (dY[0][cc] * ay[0] + dY[1][cc] * ay[1] + dY[2][cc] * ay[2]) +
+                                  (dZ[0][cc] * az[0] + dZ[1][cc] * az[1] + dZ[2][cc] * az[2]);
+                    }
+                }
+                if (bdr_on) {
+                    const double v2 = violaBdr * violaBdr, v3 = v2 * violaBdr;
+                    const double coef = w * P.chi[3] * (3.0 * v2);
+                    // dSqrMagBdr = 2 bd0 dBdr.row(0) + 2 bd1 dBdr.row(1),
+                    // dBdr = -r dfThr^T / f^2 - R^T (dxB r0 + dyB r1 + dzB r2) / f        (CPU.hpp:293-296)
+                    const double t0 = 2.0 * bd0, t1 = 2.0 * bd1;
+                    const double wv[3] = {t0 * xx + t1 * yx, t0 * xy + t1 * yy, t0 * xz + t1 * yz};
+                    const double hfac = (t0 * r0 + t1 * r1) / (sqrMagThr * fThr);
+                    const double hh[3] = {hx, hy, hz};
+                    const double Rx[3] = {xx, xy, xz}, Ry[3] = {yx, yy, yz};
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 3; m++) s += wv[m] * (dX[m][cc] * r0 + dY[m][cc] * r1 + dZ[m][cc] * r2);
+                        const double dS = -hfac * hh[cc] - s / fThr;
+                        const double dJ = (t1 * Ry[cc] + t0 * Rx[cc]) / fThr;  // dJerSqrMagBdr (CPU.hpp:297-299)
+                        g2[cc] += coef * dS;
+                        g3[cc] += coef * dJ;
+                    }
+                    cst += w * P.chi[3] * v3;
+                    direct += omg * P.chi[3] * v3 * invK;
+                }
+            }
+            if (sfc_on || bdr_on || violaVel > 0.0 || violaThrl > 0.0 || violaThrh > 0.0) {
+                // dJ/dc += beta0 (x) g0 + beta1 (x) g1 + beta2 (x) g2 + beta3 (x) g3
+                const double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+                const double b2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
+                const double b3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
+                const double b0[6] = {1.0, s1, s2, s3, s4, s5};
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    acc[0 + d] += b0[0] * g0[d];
+                    acc[3 + d] += b0[1] * g0[d] + b1[1] * g1[d];
+                    acc[6 + d] += b0[2] * g0[d] + b1[2] * g1[d] + b2[2] * g2[d];
+                    acc[9 + d] += b0[3] * g0[d] + b1[3] * g1[d] + b2[3] * g2[d] + b3[3] * g3[d];
+                    acc[12 + d] += b0[4] * g0[d] + b1[4] * g1[d] + b2[4] * g2[d] + b3[4] * g3[d];
+                    acc[15 + d] += b0[5] * g0[d] + b1[5] * g1[d] + b2[5] * g2[d] + b3[5] * g3[d];
+                }
+                // time gradient: alpha * (g0.vel + g1.acc + g2.jer + g3.sna) + the v^3/K terms
+                const double sn0 = c[12] * 24.0 + c[15] * (120.0 * s1);
+                const double sn1 = c[13] * 24.0 + c[16] * (120.0 * s1);
+                const double sn2 = c[14] * 24.0 + c[17] * (120.0 * s1);
+                acc[18] += alpha * ((g0[0] * vel[0] + g0[1] * vel[1] + g0[2] * vel[2]) +
+                                    (g1[0] * ac[0] + g1[1] * ac[1] + g1[2] * ac[2]) +
+                                    (g2[0] * jer[0] + g2[1] * jer[1] + g2[2] * jer[2]) +
+                                    (g3[0] * sn0 + g3[1] * sn1 + g3[2] * sn2)) +
+                           direct;
+                acc[19] += cst;
+            }
+            s1 += step;
+        }
+    }
+    // ---- fixed-order reduction of the per-thread partials into per-piece sums ----
+    {
+        double* mine = part + (size_t)tid * 20;
+#pragma unroll
+        for (int i = 0; i < 20; i++) mine[i] = acc[i];
+    }
+    __syncthreads();
+    for (int task = tid; task < npieces * 20; task += blockDim.x) {
+        const int p = task / 20, v = task - p * 20;
+        const int gp = gp_base + p;
+        const double* src = part + (size_t)p * pl.tpp * 20 + v;
+        double s = 0.0;
+        for (int t = 0; t < pl.tpp; t++) s += src[(size_t)t * 20];
+        const double* c = cblk + p * 18;
+        const double T1 = bv.T[gp], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        if (v < 18) {
+            // energy gradient w.r.t. c rows 3..5 (CPU.hpp:80-95), added first as in the reference
+            const int row = v / 3, d = v - 3 * row;
+            double e = 0.0;
+            const double c3 = c[9 + d], c4 = c[12 + d], c5 = c[15 + d];
+            if (row == 5) e = 240.0 * c3 * T3 + 720.0 * c4 * T4 + 1440.0 * c5 * T5;
+            if (row == 4) e = 144.0 * c3 * T2 + 384.0 * c4 * T3 + 720.0 * c5 * T4;
+            if (row == 3) e = 72.0 * c3 * T1 + 144.0 * c4 * T2 + 240.0 * c5 * T3;
+            bv.gdC[18 * (size_t)gp + v] = e + s;
+        } else {
+            const double q33 = c[9] * c[9] + c[10] * c[10] + c[11] * c[11];
+            const double q44 = c[12] * c[12] + c[13] * c[13] + c[14] * c[14];
+            const double q55 = c[15] * c[15] + c[16] * c[16] + c[17] * c[17];
+            const double q43 = c[12] * c[9] + c[13] * c[10] + c[14] * c[11];
+            const double q53 = c[15] * c[9] + c[16] * c[10] + c[17] * c[11];
+            const double q54 = c[15] * c[12] + c[16] * c[13] + c[17] * c[14];
+            if (v == 18) {  // CPU.hpp:65-77
+                const double e = 36.0 * q33 + 288.0 * q43 * T1 + 576.0 * q44 * T2 + 720.0 * q53 * T2 + 2880.0 * q54 * T3 +
+                                 3600.0 * q55 * T4;
+                bv.gdT[gp] = e + s;
+            } else {  // CPU.hpp:507-520
+                bv.energy[gp] = 36.0 * q33 * T1 + 144.0 * q43 * T2 + 192.0 * q44 * T3 + 240.0 * q53 * T3 + 720.0 * q54 * T4 +
+                                720.0 * q55 * T5;
+                bv.pen[gp] = s;
+            }
+        }
+    }
+}
+
+// K3 ---------------------------------------------------------------------------------------------
+// smem: As[N][16] (LU factors; slots 13..15 = adjoint RHS) | gT[M] | gq[3*M] | Tc-grad[coarseN]
+__global__ void __launch_bounds__(32)
+    minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
+                          double* __restrict__ grad_out) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x;
+    if (bv.active && !bv.active[b]) return;
+    const int lane = threadIdx.x;
+    const int p0 = bv.piece_off[b];
+    const int M = bv.piece_off[b + 1] - p0;
+    const int N = 6 * M;
+    const int co0 = bv.coarse_off[b];
+    const int coarseN = bv.coarse_off[b + 1] - co0;
+    const DevParams par = bv.par[b];
+    const double* x = xin + bv.x_off[b];
+    double* grad = grad_out + bv.x_off[b];
+    const int dimT = bv.dimT[b];
+    double* As = sm;
+    double* gT = As + (size_t)N * BW;
+    double* gq = gT + M;
+    double* gTc = gq + 3 * (size_t)M;
+
+    const double* lug = bv.lu + (size_t)BW * 6 * p0;
+    for (int i = lane; i < N * BW; i += 32) As[i] = lug[i];
+    __syncwarp();
+    const double* gdC = bv.gdC + 18 * (size_t)p0;
+    for (int i = lane; i < 3 * N; i += 32) As[(size_t)(i / 3) * BW + 13 + (i % 3)] = gdC[i];
+    __syncwarp();
+
+    // ---- A^T lambda = gdC (trajectory.hpp:724-751) ----
+    {
+        const int r = lane / 3, d = lane - 3 * r;
+        const bool act = lane < 18;
+        for (int j = 0; j <= N - 1; j++) {
+            double bj = 0.0;
+            if (act) bj = As[(size_t)j * BW + 13 + d] / As[(size_t)j * BW + 6];
+            __syncwarp();
+            if (act) {
+                const int i = j + 1 + r;
+                if (i < N) As[(size_t)i * BW + 13 + d] -= As[(size_t)j * BW + (7 + r)] * bj;  // A(j,i), i>j : U part of row j
+                if (r == 0) As[(size_t)j * BW + 13 + d] = bj;
+            }
+            __syncwarp();
+        }
+        for (int j = N - 1; j >= 0; j--) {
+            if (act) {
+                const double bj = As[(size_t)j * BW + 13 + d];
+                const int i = j - 1 - r;
+                if (i >= 0) As[(size_t)i * BW + 13 + d] -= As[(size_t)j * BW + (5 - r)] * bj;  // A(j,i), i<j : L part of row j
+            }
+            __syncwarp();
+        }
+    }
+    // ---- addPropCtoT (CPU.hpp:104-151), addPropCtoP (:154-161), rho (:989) ----
+    const double* cg_ = bv.c + 18 * (size_t)p0;
+    for (int i = lane; i < M; i += 32) {
+        const double T1 = bv.T[p0 + i], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2;
+        const double* c = cg_ + 18 * i;
+        double s = 0.0;
+        const int rows = (i < M - 1) ? 6 : 3;
+        const int base = (i < M - 1) ? (6 * i + 3) : (6 * M - 3);
+        for (int d = 0; d < 3; d++) {
+            const double c1 = c[3 + d], c2 = c[6 + d], c3 = c[9 + d], c4 = c[12 + d], c5 = c[15 + d];
+            const double nVel = -(c1 + 2.0 * T1 * c2 + 3.0 * T2 * c3 + 4.0 * T3 * c4 + 5.0 * T4 * c5);
+            const double nAcc = -(2.0 * c2 + 6.0 * T1 * c3 + 12.0 * T2 * c4 + 20.0 * T3 * c5);
+            const double nJer = -(6.0 * c3 + 24.0 * T1 * c4 + 60.0 * T2 * c5);
+            if (rows == 6) {
+                const double nSnp = -(24.0 * c4 + 120.0 * T1 * c5);
+                const double nCrk = -120.0 * c5;
+                const double B1[6] = {nSnp, nCrk, nVel, nVel, nAcc, nJer};
+                for (int r = 0; r < 6; r++) s += B1[r] * As[(size_t)(base + r) * BW + 13 + d];
+            } else {
+                const double B2[3] = {nVel, nAcc, nJer};
+                for (int r = 0; r < 3; r++) s += B2[r] * As[(size_t)(base + r) * BW + 13 + d];
+            }
+        }
+        gT[i] = bv.gdT[p0 + i] + s + par.rho;
+        if (i < M - 1)
+            for (int d = 0; d < 3; d++) gq[3 * i + d] = As[(size_t)(6 * i + 5) * BW + 13 + d];
+    }
+    __syncwarp();
+    // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope ----
+    if (lane == 0) {
+        int offset = 0;
+        for (int i = 0; i < coarseN; i++) {
+            const int iv = bv.intervals[co0 + i];
+            double s = 0.0;
+            for (int a = 0; a < iv; a++) s += gT[offset + a];
+            gTc[i] = s / iv;
+            offset += iv;
+        }
+    }
+    __syncwarp();
+    // ---- addLayerTGrad (CPU.hpp:816-894) ----
+    if (par.softT) {
+        for (int i = lane; i < dimT; i += 32) {
+            const double t = x[i];
+            double g = gTc[i];
+            if (par.c2) {
+                if (t > 0)
+                    g *= t + 1.0;
+                else {
+                    const double den = (0.5 * t - 1.0) * t + 1.0;
+                    g *= (1.0 - t) / (den * den);
+                }
+            } else
+                g *= exp(t);
+            grad[i] = g;
+        }
+    } else if (lane == 0) {
+        const int Ms1 = dimT;
+        const double gTail = par.sumT * gTc[Ms1];
+        double expTauSum = 0.0, gFreeDotExpTau = 0.0;
+        for (int i = 0; i < Ms1; i++) {
+            const double t = x[i];
+            const double gFree = par.sumT * gTc[i];
+            double eTau;
+            if (par.c2) {
+                if (t > 0)
+                    eTau = (0.5 * t + 1.0) * t + 1.0;
+                else
+                    eTau = 1.0 / ((0.5 * t - 1.0) * t + 1.0);
+            } else
+                eTau = exp(t);
+            expTauSum += eTau;
+            gFreeDotExpTau += eTau * gFree;
+        }
+        const double den = expTauSum + 1.0;
+        for (int i = 0; i < Ms1; i++) {
+            const double t = x[i];
+            const double gFree = par.sumT * gTc[i];
+            double dE;
+            if (par.c2) {
+                if (t > 0)
+                    dE = t + 1.0;
+                else {
+                    const double ds = (0.5 * t - 1.0) * t + 1.0;
+                    dE = (1.0 - t) / (ds * ds);
+                }
+            } else
+                dE = exp(t);
+            grad[i] = (gFree - gTail) * dE / den - (gFreeDotExpTau - gTail * expTauSum) * dE / (den * den);
+        }
+    }
+    // ---- addLayerPGrad (CPU.hpp:897-928) ----
+    for (int i = lane; i < M - 1; i += 32) {
+        const int k = bv.wp_vert_cnt[p0 + i] - 1;
+        const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
+        const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
+        double* gxi = grad + dimT + bv.wp_xi_off[p0 + i];
+        double qn = 0.0;
+        for (int a = 0; a < k; a++) qn += xi[a] * xi[a];
+        const double q1 = qn + 1.0, q1s = q1 * q1;
+        const double gx = gq[3 * i], gy = gq[3 * i + 1], gz = gq[3 * i + 2];
+        double gdot = 0.0;
+        for (int a = 0; a < k; a++) {
+            const double r = 2.0 / q1 * xi[a];
+            const double gd = (V[3 * (a + 1)] * gx + V[3 * (a + 1) + 1] * gy + V[3 * (a + 1) + 2] * gz) * r * 2.0;
+            gdot += gd * xi[a];
+        }
+        for (int a = 0; a < k; a++) {
+            const double r = 2.0 / q1 * xi[a];
+            const double gd = (V[3 * (a + 1)] * gx + V[3 * (a + 1) + 1] * gy + V[3 * (a + 1) + 2] * gz) * r * 2.0;
+            gxi[a] = gd * 2.0 / q1 - xi[a] * 4.0 * gdot / q1s;
+        }
+    }
+    // ---- cost = jerk energy + penalty + rho * sum(T) (CPU.hpp:542,406,988), sequential sums ----
+    if (lane == 0) {
+        double e = 0.0, pn = 0.0;
+        for (int i = 0; i < M; i++) e += bv.energy[p0 + i];
+        for (int i = 0; i < M; i++) pn += bv.pen[p0 + i];
+        double cost = e + pn;
+        double sT = 0.0;
+        if (par.softT) {
+            for (int i = 0; i < coarseN; i++) sT += par.c2 ? c2_forward(x[i]) : exp(x[i]);
+        } else {
+            // coarse T of the fixed-total-time map: recover from the fine T (sum over pieces of a polytope)
+            for (int i = 0; i < M; i++) sT += bv.T[p0 + i];
+        }
+        cost_out[b] = cost + par.rho * sT;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side launchers
+// ------------------------------------------------------------------------------------------------
+size_t forward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)18 * M + coarseN + 1); }
+size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)4 * M + coarseN + 1); }
+
+PenaltyLaunch plan_penalty(const BatchView& bv) {
+    PenaltyLaunch pl;
+    const int S = bv.max_samples;
+    // samples per thread: aim for <= 16 threads per piece, pick the split that wastes fewest slots
+    int best_spt = (S + 15) / 16, best_waste = 1 << 30;
+    for (int spt = (S + 15) / 16; spt <= (S + 15) / 16 + 2; spt++) {
+        const int tpp = (S + spt - 1) / spt;
+        const int waste = tpp * spt - S;
+        if (waste < best_waste) best_waste = waste, best_spt = spt;
+    }
+    pl.spt = best_spt;
+    pl.tpp = (S + pl.spt - 1) / pl.spt;
+    pl.threads = 256;
+    pl.ppc = pl.threads / pl.tpp;
+    if (pl.ppc < 1) pl.ppc = 1;
+    pl.grid = (bv.total_pieces + pl.ppc - 1) / pl.ppc;
+    pl.smem = sizeof(double) * ((size_t)pl.ppc * 18 + (size_t)pl.ppc * 6 * bv.max_faces + (size_t)pl.threads * 20);
+    return pl;
+}
+
+cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(minco_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(minco_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(penalty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pen_smem);
+    return e;
+}
+
+cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                        const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
+    minco_forward_kernel<<<bv.B, 32, fwd_smem, st>>>(bv, x_dev);
+    penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
+    minco_backward_kernel<<<bv.B, 32, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+    return cudaGetLastError();
+}
+
+}  // namespace frx

@@ -1,0 +1,533 @@
+// Implementation of the C ABI declared in include/frx.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "../../include/frx.h"
+#include "device_batch.cuh"
+#include "host_model.hpp"
+#include "solver.cuh"
+
+namespace frx {
+size_t forward_smem_bytes(int M, int coarseN);
+size_t backward_smem_bytes(int M, int coarseN);
+PenaltyLaunch plan_penalty(const BatchView& bv);
+cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);
+cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                        const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st);
+}  // namespace frx
+
+using namespace frx;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t alloc(size_t n) {
+        bytes = n ? n : 8;
+        return cudaMalloc(&p, bytes);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+struct frx_batch {
+    int device = 0;
+    std::vector<TrajectoryModel> models;
+    std::vector<int> piece_off, x_off, coarse_off;
+    int max_M = 0, max_coarse = 0;
+    BatchView bv{};
+    PenaltyLaunch pl{};
+    size_t fwd_smem = 0, bwd_smem = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    std::vector<DevBuf> bufs;
+    // persistent device-side x / cost / grad for the host-buffer API
+    double *x_dev = nullptr, *g_dev = nullptr, *cost_dev = nullptr;
+    double *x_pin = nullptr, *g_pin = nullptr, *cost_pin = nullptr;
+    SolverState* solver = nullptr;  // lazily created by frx_batch_optimize
+    // result of the last optimize (for argmin)
+    double* final_cost_dev = nullptr;
+    bool have_final = false;
+
+    template <class T>
+    cudaError_t upload(const std::vector<T>& h, const T** out) {
+        DevBuf b;
+        cudaError_t e = b.alloc(sizeof(T) * h.size());
+        if (e != cudaSuccess) return e;
+        bufs.push_back(b);
+        if (!h.empty()) e = cudaMemcpy(b.p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice);
+        *out = (const T*)b.p;
+        return e;
+    }
+    template <class T>
+    cudaError_t scratch(size_t n, T** out) {
+        DevBuf b;
+        cudaError_t e = b.alloc(sizeof(T) * n);
+        if (e != cudaSuccess) return e;
+        bufs.push_back(b);
+        e = cudaMemset(b.p, 0, b.bytes);
+        *out = (T*)b.p;
+        return e;
+    }
+};
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    std::fprintf(stderr, "[frx] CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+    return FRX_ERR_CUDA;
+}
+#define CK(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+extern "C" {
+
+const char* frx_version(void) { return "fast_racing_b200 0.1 (sm_100a)"; }
+
+const char* frx_strerror(int s) {
+    switch (s) {
+    case FRX_OK: return "ok";
+    case FRX_ERR_INVALID_ARG: return "invalid argument";
+    case FRX_ERR_INFEASIBLE_GEOMETRY: return "infeasible geometry: a polytope or a consecutive intersection has no interior";
+    case FRX_ERR_CUDA: return "CUDA error or no usable CUDA device (there is no CPU fallback)";
+    case FRX_ERR_CAPACITY: return "problem exceeds a kernel capacity limit";
+    case FRX_ERR_NOMEM: return "out of memory";
+    default: return s <= -1001 && s >= -1024 ? "L-BFGS status (see lbfgs.hpp:148-205)" : "unknown";
+    }
+}
+
+void frx_batch_destroy(frx_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->solver) solver_destroy(b->solver);
+    for (auto& d : b->bufs) d.release();
+    if (b->x_pin) cudaFreeHost(b->x_pin);
+    if (b->g_pin) cudaFreeHost(b->g_pin);
+    if (b->cost_pin) cudaFreeHost(b->cost_pin);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int frx_batch_create(const frx_problem* problems, int count, int device_ordinal, frx_batch** out) {
+    if (!problems || count < 1 || !out) return FRX_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        std::fprintf(stderr, "[frx] no CUDA device: this library has no CPU fallback\n");
+        return FRX_ERR_CUDA;
+    }
+    frx_batch* b = new (std::nothrow) frx_batch();
+    if (!b) return FRX_ERR_NOMEM;
+    if (device_ordinal < 0) {
+        if (cudaGetDevice(&b->device) != cudaSuccess) {
+            delete b;
+            return FRX_ERR_CUDA;
+        }
+    } else
+        b->device = device_ordinal;
+    if (cudaSetDevice(b->device) != cudaSuccess) {
+        delete b;
+        return FRX_ERR_CUDA;
+    }
+    // ---- host models (geometry + tables), in parallel over problems ----
+    b->models.resize(count);
+    std::vector<int> status(count, FRX_OK);
+    {
+        const int nt = std::max(1, std::min<int>(std::thread::hardware_concurrency(), std::min(count, 32)));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; t++)
+            pool.emplace_back([&, t]() {
+                for (int i = t; i < count; i += nt) status[i] = build_model(problems[i], b->models[i]);
+            });
+        for (auto& th : pool) th.join();
+    }
+    for (int i = 0; i < count; i++)
+        if (status[i] != FRX_OK) {
+            const int s = status[i];
+            delete b;
+            return s;
+        }
+    // ---- pack ----
+    const int B = count;
+    b->piece_off.assign(B + 1, 0);
+    b->x_off.assign(B + 1, 0);
+    b->coarse_off.assign(B + 1, 0);
+    for (int i = 0; i < B; i++) {
+        const TrajectoryModel& m = b->models[i];
+        b->piece_off[i + 1] = b->piece_off[i] + m.fineN;
+        b->x_off[i + 1] = b->x_off[i] + m.n();
+        b->coarse_off[i + 1] = b->coarse_off[i] + m.coarseN;
+        b->max_M = std::max(b->max_M, m.fineN);
+        b->max_coarse = std::max(b->max_coarse, m.coarseN);
+    }
+    const int TP = b->piece_off[B];
+    std::vector<int> dimT(B), intervals, piece_traj(TP), piece_poly(TP), cons(TP), pf_off(TP), pf_cnt(TP), wv_off(TP), wv_cnt(TP), wxi(TP);
+    std::vector<DevParams> par(B);
+    std::vector<double> headtail(18 * (size_t)B), faces, verts;
+    int max_faces = 0, max_samples = 0;
+    for (int i = 0; i < B; i++) {
+        const TrajectoryModel& m = b->models[i];
+        dimT[i] = m.dimT;
+        DevParams& P = par[i];
+        P.rho = m.rho, P.sumT = m.sumT;
+        P.ell[0] = m.par.horiz_half_len, P.ell[1] = m.par.horiz_half_len, P.ell[2] = m.par.vert_half_len;
+        P.margin = m.par.safe_margin;
+        P.vmax_sqr = m.par.v_max * m.par.v_max;
+        P.thrmin_sqr = m.par.thr_acc_min * m.par.thr_acc_min;
+        P.thrmax_sqr = m.par.thr_acc_max * m.par.thr_acc_max;
+        P.bdrmax_sqr = m.par.body_rate_max * m.par.body_rate_max;
+        P.gacc = m.par.grav_acc;
+        for (int q = 0; q < 4; q++) P.chi[q] = m.par.chi[q];
+        P.softT = m.softT, P.c2 = m.c2;
+        std::memcpy(&headtail[18 * (size_t)i], m.ini, 9 * sizeof(double));
+        std::memcpy(&headtail[18 * (size_t)i + 9], m.fin, 9 * sizeof(double));
+        intervals.insert(intervals.end(), m.intervals.begin(), m.intervals.end());
+        const int face_base = (int)(faces.size() / 6);
+        faces.insert(faces.end(), m.faces.begin(), m.faces.end());
+        std::vector<int> vbase(m.vpolys.size());
+        for (size_t v = 0; v < m.vpolys.size(); v++) {
+            vbase[v] = (int)(verts.size() / 3);
+            verts.insert(verts.end(), m.vpolys[v].v.begin(), m.vpolys[v].v.end());
+        }
+        for (int p = 0; p < m.fineN; p++) {
+            const int gp = b->piece_off[i] + p;
+            piece_traj[gp] = i;
+            piece_poly[gp] = m.idxHs[p];
+            cons[gp] = m.cons[p];
+            pf_off[gp] = face_base + m.face_off[m.idxHs[p]];
+            pf_cnt[gp] = m.face_off[m.idxHs[p] + 1] - m.face_off[m.idxHs[p]];
+            max_faces = std::max(max_faces, pf_cnt[gp]);
+            max_samples = std::max(max_samples, m.cons[p] + 1);
+            if (p < m.fineN - 1) {
+                wv_off[gp] = vbase[m.idxVs[p]];
+                wv_cnt[gp] = m.vpolys[m.idxVs[p]].cols();
+                wxi[gp] = m.xi_off[p];
+            } else {
+                wv_off[gp] = 0, wv_cnt[gp] = 0, wxi[gp] = m.dimP;
+            }
+        }
+    }
+    BatchView& bv = b->bv;
+    bv.B = B, bv.total_pieces = TP, bv.total_x = b->x_off[B];
+    bv.max_faces = max_faces, bv.max_samples = max_samples;
+    b->fwd_smem = forward_smem_bytes(b->max_M, b->max_coarse);
+    b->bwd_smem = backward_smem_bytes(b->max_M, b->max_coarse);
+    if (b->fwd_smem > 227 * 1024 || b->bwd_smem > 227 * 1024) {
+        delete b;
+        return FRX_ERR_CAPACITY;  // band system of one trajectory must fit the shared memory of one SM
+    }
+    auto fail = [&](cudaError_t e, const char* what) {
+        int r = cuda_fail(e, what);
+        frx_batch_destroy(b);
+        return r;
+    };
+    cudaError_t e;
+#define UP(vec, field)                                             \
+    if ((e = b->upload(vec, &bv.field)) != cudaSuccess) return fail(e, "upload " #field)
+    UP(b->piece_off, piece_off);
+    UP(b->x_off, x_off);
+    UP(b->coarse_off, coarse_off);
+    UP(dimT, dimT);
+    UP(par, par);
+    UP(headtail, headtail);
+    UP(intervals, intervals);
+    UP(piece_traj, piece_traj);
+    UP(piece_poly, piece_poly);
+    UP(cons, cons);
+    UP(pf_off, piece_face_off);
+    UP(pf_cnt, piece_face_cnt);
+    UP(wv_off, wp_vert_off);
+    UP(wv_cnt, wp_vert_cnt);
+    UP(wxi, wp_xi_off);
+    UP(faces, faces);
+    UP(verts, verts);
+#undef UP
+#define SC(n, field)                                                \
+    if ((e = b->scratch((size_t)(n), &bv.field)) != cudaSuccess) return fail(e, "alloc " #field)
+    SC(TP, T);
+    SC(3 * (size_t)TP, q);
+    SC(18 * (size_t)TP, c);
+    SC(96 * (size_t)TP, lu);
+    SC(18 * (size_t)TP, gdC);
+    SC(TP, gdT);
+    SC(TP, pen);
+    SC(TP, energy);
+#undef SC
+    if ((e = b->scratch((size_t)bv.total_x, &b->x_dev)) != cudaSuccess) return fail(e, "alloc x");
+    if ((e = b->scratch((size_t)bv.total_x, &b->g_dev)) != cudaSuccess) return fail(e, "alloc g");
+    if ((e = b->scratch((size_t)B, &b->cost_dev)) != cudaSuccess) return fail(e, "alloc cost");
+    if ((e = b->scratch((size_t)B, &b->final_cost_dev)) != cudaSuccess) return fail(e, "alloc final cost");
+    if ((e = cudaMallocHost(&b->x_pin, sizeof(double) * bv.total_x)) != cudaSuccess) return fail(e, "pinned x");
+    if ((e = cudaMallocHost(&b->g_pin, sizeof(double) * bv.total_x)) != cudaSuccess) return fail(e, "pinned g");
+    if ((e = cudaMallocHost(&b->cost_pin, sizeof(double) * B)) != cudaSuccess) return fail(e, "pinned cost");
+    if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
+    if ((e = cudaEventCreate(&b->ev0)) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaEventCreate(&b->ev1)) != cudaSuccess) return fail(e, "event");
+    b->pl = plan_penalty(bv);
+    if (b->pl.smem > 227 * 1024) {
+        frx_batch_destroy(b);
+        return FRX_ERR_CAPACITY;
+    }
+    if ((e = configure_kernels(b->fwd_smem, b->bwd_smem, b->pl.smem)) != cudaSuccess) return fail(e, "configure kernels");
+    *out = b;
+    return FRX_OK;
+}
+
+int frx_batch_count(const frx_batch* b) { return b ? b->bv.B : FRX_ERR_INVALID_ARG; }
+
+int frx_batch_dims(const frx_batch* b, int traj, int* n, int* pieces, int* dim_t, int* dim_p) {
+    if (!b || traj < 0 || traj >= b->bv.B) return FRX_ERR_INVALID_ARG;
+    const TrajectoryModel& m = b->models[traj];
+    if (n) *n = m.n();
+    if (pieces) *pieces = m.fineN;
+    if (dim_t) *dim_t = m.dimT;
+    if (dim_p) *dim_p = m.dimP;
+    return FRX_OK;
+}
+int frx_batch_x_offsets(const frx_batch* b, int* off) {
+    if (!b || !off) return FRX_ERR_INVALID_ARG;
+    std::copy(b->x_off.begin(), b->x_off.end(), off);
+    return FRX_OK;
+}
+int frx_batch_piece_offsets(const frx_batch* b, int* off) {
+    if (!b || !off) return FRX_ERR_INVALID_ARG;
+    std::copy(b->piece_off.begin(), b->piece_off.end(), off);
+    return FRX_OK;
+}
+int frx_batch_tables(const frx_batch* b, int traj, int* intervals, int* idx_hs, int* idx_vs, int* cons) {
+    if (!b || traj < 0 || traj >= b->bv.B) return FRX_ERR_INVALID_ARG;
+    const TrajectoryModel& m = b->models[traj];
+    if (intervals) std::copy(m.intervals.begin(), m.intervals.end(), intervals);
+    if (idx_hs) std::copy(m.idxHs.begin(), m.idxHs.end(), idx_hs);
+    if (idx_vs) std::copy(m.idxVs.begin(), m.idxVs.end(), idx_vs);
+    if (cons) std::copy(m.cons.begin(), m.cons.end(), cons);
+    return FRX_OK;
+}
+int frx_batch_vpolys(const frx_batch* b, int traj, int* vert_off, double* verts) {
+    if (!b || traj < 0 || traj >= b->bv.B || !vert_off) return FRX_ERR_INVALID_ARG;
+    const TrajectoryModel& m = b->models[traj];
+    int off = 0;
+    for (size_t v = 0; v < m.vpolys.size(); v++) {
+        vert_off[v] = off;
+        if (verts) std::copy(m.vpolys[v].v.begin(), m.vpolys[v].v.end(), verts + 3 * (size_t)off);
+        off += m.vpolys[v].cols();
+    }
+    vert_off[m.vpolys.size()] = off;
+    return FRX_OK;
+}
+
+int frx_batch_initial_guess(frx_batch* b, double* x_host) {
+    if (!b || !x_host) return FRX_ERR_INVALID_ARG;
+    const int B = b->bv.B;
+    const int nt = std::max(1, std::min<int>(std::thread::hardware_concurrency(), std::min(B, 32)));
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++)
+        pool.emplace_back([&, t]() {
+            for (int i = t; i < B; i += nt) initial_guess(b->models[i], x_host + b->x_off[i]);
+        });
+    for (auto& th : pool) th.join();
+    return FRX_OK;
+}
+
+int frx_batch_eval_launches(const frx_batch* b) { return b ? 3 : FRX_ERR_INVALID_ARG; }
+
+int frx_batch_eval_device(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream) {
+    if (!b || !x_dev || !cost_dev || !grad_dev) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, st));
+    return FRX_OK;
+}
+
+int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double* grad_host) {
+    if (!b || !x_host || !cost_host || !grad_host) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    const size_t nx = sizeof(double) * (size_t)b->bv.total_x;
+    std::memcpy(b->x_pin, x_host, nx);
+    CK(cudaEventRecord(b->ev0, b->stream));
+    CK(cudaMemcpyAsync(b->x_dev, b->x_pin, nx, cudaMemcpyHostToDevice, b->stream));
+    CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, b->x_dev, b->cost_dev, b->g_dev, b->stream));
+    CK(cudaMemcpyAsync(b->g_pin, b->g_dev, nx, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->cost_pin, b->cost_dev, sizeof(double) * b->bv.B, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    b->last_ms = ms;
+    std::memcpy(grad_host, b->g_pin, nx);
+    std::memcpy(cost_host, b->cost_pin, sizeof(double) * b->bv.B);
+    return FRX_OK;
+}
+
+double frx_eval(void* instance, const double* x, double* g, const int n) {
+    frx_batch* b = (frx_batch*)instance;
+    if (!b || b->bv.B != 1 || n != b->bv.total_x) return NAN;
+    double cost = NAN;
+    if (frx_batch_eval(b, x, &cost, g) != FRX_OK) return NAN;
+    return cost;
+}
+
+double frx_batch_last_ms(const frx_batch* b) { return b ? b->last_ms : -1.0; }
+
+// Intermediate device quantities of the last evaluation (for component-level parity tests):
+// T[pieces], q[3*pieces] (last slot unused), c[18*pieces], gdC_lambda[18*pieces], pen[pieces], energy[pieces], gdT[pieces]
+int frx_batch_debug_fetch(frx_batch* b, double* T, double* q, double* c, double* lambda, double* pen, double* energy,
+                          double* gdT) {
+    if (!b) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    const size_t TP = b->bv.total_pieces;
+    if (T) CK(cudaMemcpy(T, b->bv.T, sizeof(double) * TP, cudaMemcpyDeviceToHost));
+    if (q) CK(cudaMemcpy(q, b->bv.q, sizeof(double) * 3 * TP, cudaMemcpyDeviceToHost));
+    if (c) CK(cudaMemcpy(c, b->bv.c, sizeof(double) * 18 * TP, cudaMemcpyDeviceToHost));
+    if (lambda) CK(cudaMemcpy(lambda, b->bv.gdC, sizeof(double) * 18 * TP, cudaMemcpyDeviceToHost));
+    if (pen) CK(cudaMemcpy(pen, b->bv.pen, sizeof(double) * TP, cudaMemcpyDeviceToHost));
+    if (energy) CK(cudaMemcpy(energy, b->bv.energy, sizeof(double) * TP, cudaMemcpyDeviceToHost));
+    if (gdT) CK(cudaMemcpy(gdT, b->bv.gdT, sizeof(double) * TP, cudaMemcpyDeviceToHost));
+    return FRX_OK;
+}
+
+// Host-only geometry entry point (no GPU needed): vertices of one H-polytope, for the CPU test tier.
+int frx_enumerate_vertices(const double* faces, int F, double* out, int cap) {
+    if (!faces || F < 4) return FRX_ERR_INVALID_ARG;
+    std::vector<double> f(faces, faces + 6 * (size_t)F), v;
+    for (int k = 0; k < F; k++) {
+        double* n = &f[6 * (size_t)k];
+        const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] /= nn, n[1] /= nn, n[2] /= nn;
+    }
+    if (!enumerate_vertices(f.data(), F, v)) return FRX_ERR_INFEASIBLE_GEOMETRY;
+    const int V = (int)v.size() / 3;
+    for (int i = 0; i < V && i < cap; i++)
+        for (int d = 0; d < 3; d++) out[3 * i + d] = v[3 * (size_t)i + d];
+    return V;
+}
+
+// Host-only: index tables + starting point of one problem without touching the GPU (CPU test tier).
+int frx_host_model(const frx_problem* p, int* n, int* pieces, int* dim_t, int* dim_p, int* intervals, int* idx_hs,
+                   int* idx_vs, int* cons, double* x0) {
+    if (!p) return FRX_ERR_INVALID_ARG;
+    TrajectoryModel m;
+    const int s = build_model(*p, m);
+    if (s != FRX_OK) return s;
+    if (n) *n = m.n();
+    if (pieces) *pieces = m.fineN;
+    if (dim_t) *dim_t = m.dimT;
+    if (dim_p) *dim_p = m.dimP;
+    if (intervals) std::copy(m.intervals.begin(), m.intervals.end(), intervals);
+    if (idx_hs) std::copy(m.idxHs.begin(), m.idxHs.end(), idx_hs);
+    if (idx_vs) std::copy(m.idxVs.begin(), m.idxVs.end(), idx_vs);
+    if (cons) std::copy(m.cons.begin(), m.cons.end(), cons);
+    if (x0) initial_guess(m, x0);
+    return FRX_OK;
+}
+// Host-only: V-polytopes of one problem (sizes: vert_off[2*n_poly]; verts may be NULL).
+int frx_host_vpolys(const frx_problem* p, int* vert_off, double* verts) {
+    if (!p || !vert_off) return FRX_ERR_INVALID_ARG;
+    TrajectoryModel m;
+    const int s = build_model(*p, m);
+    if (s != FRX_OK) return s;
+    int off = 0;
+    for (size_t v = 0; v < m.vpolys.size(); v++) {
+        vert_off[v] = off;
+        if (verts) std::copy(m.vpolys[v].v.begin(), m.vpolys[v].v.end(), verts + 3 * (size_t)off);
+        off += m.vpolys[v].cols();
+    }
+    vert_off[m.vpolys.size()] = off;
+    return FRX_OK;
+}
+
+int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* coeffs, double* jerk_cost,
+                       double* final_cost, int* lbfgs_status, int* iterations, int* evaluations, double* x_final) {
+    if (!b) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    // starting point: setInitial + backwardT/P on the host, one H2D copy
+    std::vector<double> x0((size_t)b->bv.total_x);
+    int s = frx_batch_initial_guess(b, x0.data());
+    if (s != FRX_OK) return s;
+    if (!b->solver) {
+        s = solver_create(b->bv, b->x_off, &b->solver);
+        if (s != FRX_OK) return s;
+    }
+    SolverIO io;
+    io.x0_host = x0.data();
+    io.rel_tol = rel_tol;
+    io.stream = b->stream;
+    auto eval = [b](const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
+        return launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, st);
+    };
+    CK(cudaEventRecord(b->ev0, b->stream));
+    s = solver_run(b->solver, b->bv, io, eval);
+    if (s != FRX_OK) return s;
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    b->last_ms = ms;
+    // outputs
+    const int B = b->bv.B;
+    const size_t TP = b->bv.total_pieces;
+    s = solver_fetch(b->solver, final_cost, lbfgs_status, iterations, evaluations, x_final);
+    if (s != FRX_OK) return s;
+    CK(cudaMemcpy(b->final_cost_dev, solver_final_cost_dev(b->solver), sizeof(double) * B, cudaMemcpyDeviceToDevice));
+    b->have_final = true;
+    // final trajectory: the last forward pass of the solver was at the final iterate (solver_run
+    // re-runs K1 on x_final, CPU.hpp:1258-1262), so T / c / energy are current.
+    std::vector<double> T(TP), c(18 * TP), en(TP);
+    CK(cudaMemcpy(T.data(), b->bv.T, sizeof(double) * TP, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c.data(), b->bv.c, sizeof(double) * 18 * TP, cudaMemcpyDeviceToHost));
+    if (durations) std::copy(T.begin(), T.end(), durations);
+    if (coeffs) {
+        // Piece(T_i, b.block<6,3>(6i,0)^T.rowwise().reverse()) : 3x6 column-major, highest order first (CPU.hpp:561)
+        for (size_t i = 0; i < TP; i++)
+            for (int col = 0; col < 6; col++)
+                for (int d = 0; d < 3; d++) coeffs[18 * i + 3 * col + d] = c[18 * i + 3 * (5 - col) + d];
+    }
+    if (jerk_cost) {
+        // getTrajJerkCost (CPU.hpp:507-520) on the final coefficients, sequential sum as the reference
+        for (int t = 0; t < B; t++) {
+            double obj = 0.0;
+            for (int i = b->piece_off[t]; i < b->piece_off[t + 1]; i++) {
+                const double* cc = &c[18 * (size_t)i];
+                const double T1 = T[i], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+                const double q33 = cc[9] * cc[9] + cc[10] * cc[10] + cc[11] * cc[11];
+                const double q44 = cc[12] * cc[12] + cc[13] * cc[13] + cc[14] * cc[14];
+                const double q55 = cc[15] * cc[15] + cc[16] * cc[16] + cc[17] * cc[17];
+                const double q43 = cc[12] * cc[9] + cc[13] * cc[10] + cc[14] * cc[11];
+                const double q53 = cc[15] * cc[9] + cc[16] * cc[10] + cc[17] * cc[11];
+                const double q54 = cc[15] * cc[12] + cc[16] * cc[13] + cc[17] * cc[14];
+                obj += 36.0 * q33 * T1 + 144.0 * q43 * T2 + 192.0 * q44 * T3 + 240.0 * q53 * T3 + 720.0 * q54 * T4 + 720.0 * q55 * T5;
+            }
+            jerk_cost[t] = obj;
+        }
+    }
+    return FRX_OK;
+}
+
+int frx_batch_solver_ticks(const frx_batch* b) { return (b && b->solver) ? solver_ticks(b->solver) : 0; }
+
+int frx_batch_argmin(frx_batch* b, int* best_traj, double* best_cost) {
+    if (!b || !b->have_final) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    int idx = -1;
+    double val = 0.0;
+    int s = solver_argmin(b->solver, b->final_cost_dev, b->bv.B, b->stream, &idx, &val);
+    if (s != FRX_OK) return s;
+    if (best_traj) *best_traj = idx;
+    if (best_cost) *best_cost = val;
+    return FRX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Batched device-side L-BFGS: replaces lbfgs::lbfgs_optimize (lbfgs.hpp:1103-1444) as called by
+// SE3GCOPTER::optimize (CPU.hpp:1243-1256) for every trajectory of a batch at once.
+//
+// Design ("lockstep ticks"): the evaluator cannot be called back from inside a line search on the
+// device, so every trajectory carries a resumable line-search state (lbfgs_core.cuh).  One tick =
+//   (1) the three evaluation kernels on the current trial points of all unfinished trajectories,
+//   (2) lbfgs_update_kernel: one CTA per trajectory consumes (f, g): directional derivative,
+//       More-Thuente / backtracking transition, and — when a line search finishes — convergence
+//       tests, (s, y) history update, two-loop recursion and the first trial point of the next
+//       iteration.  Finished trajectories are masked out of all four kernels.
+// The host only polls a device counter of unfinished trajectories every few ticks.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/frx.h"
+#include "device_batch.cuh"
+#include "lbfgs_core.cuh"
+
+namespace frx {
+
+enum : int { PH_INIT = 0, PH_MT = 1, PH_BT = 2, PH_DONE = 3 };
+
+struct TrajSolve {  // per-trajectory scalar state, lives in global memory
+    LineSearch ls;
+    int phase, status, k, end, n_evals, pad;
+    double fx, fp, step, stepp;
+    double pf[8];  // ring of past objective values (past <= 8)
+};
+
+struct SolverView {
+    int B;
+    LbfgsConfig cfg;
+    const int* x_off;   // B+1
+    TrajSolve* st;      // B
+    int* active;        // B: 1 while the trajectory still wants evaluations (read by the eval kernels)
+    int* n_active;      // 1
+    double *x, *g, *cost;          // current trial point / gradient / objective (packed)
+    double *xp, *gp, *d;           // previous iterate, its gradient, search direction
+    double *S, *Y;                 // history: trajectory b, slot j at mem_size*x_off[b] + j*n_b
+    double *ys, *alpha;            // mem_size per trajectory
+};
+
+struct SolverState;
+
+struct SolverIO {
+    const double* x0_host = nullptr;
+    double rel_tol = 1e-5;
+    cudaStream_t stream = nullptr;
+    int max_ticks = 400000;  // safety net only; the reference has no iteration limit (max_iterations = 0)
+    int poll_every = 8;
+};
+
+int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverState** out);
+void solver_destroy(SolverState* s);
+SolverView& solver_view(SolverState* s);
+int solver_reset(SolverState* s, const SolverIO& io);                       // uploads x0, zeroes the state
+cudaError_t solver_launch_update(SolverState* s, cudaStream_t st);          // one lbfgs_update_kernel launch
+int solver_poll_active(SolverState* s, cudaStream_t st, int* n_active);     // sync + read the counter
+int solver_fetch(SolverState* s, double* final_cost, int* status, int* iters, int* evals, double* x_final);
+const double* solver_final_cost_dev(SolverState* s);
+int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st, int* idx, double* val);
+int solver_ticks(SolverState* s);
+void solver_set_ticks(SolverState* s, int t);
+void solver_bind_active(BatchView& bv, SolverState* s, bool on);
+
+// Runs the solve.  `eval(x_dev, cost_dev, grad_dev, stream)` launches one batched evaluation.
+template <class Eval>
+int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, Eval&& eval) {
+    int r = solver_reset(s, io);
+    if (r != FRX_OK) return r;
+    SolverView& sv = solver_view(s);
+    solver_bind_active(bv, s, true);
+    int ticks = 0, n_active = bv.B;
+    while (n_active > 0 && ticks < io.max_ticks) {
+        for (int t = 0; t < io.poll_every; t++) {
+            if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            ticks++;
+        }
+        r = solver_poll_active(s, io.stream, &n_active);
+        if (r != FRX_OK) return r;
+    }
+    solver_set_ticks(s, ticks);
+    // final forward pass at the final iterates of ALL trajectories (CPU.hpp:1258-1262)
+    solver_bind_active(bv, s, false);
+    if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+    return FRX_OK;
+}
+
+}  // namespace frx

@@ -1,0 +1,141 @@
+/*
+ * frx.h — C ABI of the B200-native MINCO / SE(3)-GCOPTER trajectory-optimisation back end.
+ *
+ * This is the drop-in boundary for ONE hot path of ZJU-FAST-Lab/Fast-Racing: the L-BFGS
+ * cost-and-gradient evaluation of SE3GCOPTER (and the L-BFGS solve that drives it), batched over
+ * independent candidate trajectories.  Plain pointers and sizes only; no C++/torch types.
+ * "CPU.hpp" below = src/plan_manage/include/se3gcopter/se3gcopter_cpu.hpp of the reference,
+ * "lbfgs.hpp" = src/plan_manage/include/se3gcopter/lbfgs.hpp, "cc.cuh" =
+ * src/plan_manage/include/cuda_computer.cuh.
+ *
+ * Conventions
+ *  - fp64 everywhere; integer tables are 32-bit int (the reference uses Eigen::VectorXi).
+ *  - 3x3 states are column-major [p v a] (Eigen default), faces are (nx,ny,nz,px,py,pz) = one
+ *    column of the reference's 6xF half-space matrix (MinCoPlan_CPU.cpp:101).
+ *  - Every function returns an int status: 0 = ok, FRX_ERR_* < 0 otherwise (L-BFGS status codes
+ *    keep the numeric values of lbfgs.hpp:148-205).  No exceptions or exit() cross this ABI
+ *    (the reference's CUDA path calls exit(1), cc.cuh:35-45).
+ *  - There is NO CPU fallback: if no CUDA device is usable every compute entry point returns
+ *    FRX_ERR_CUDA.
+ *  - A frx_batch is not thread-safe; distinct batches are independent (each owns its stream).
+ */
+#ifndef FRX_H_
+#define FRX_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRX_OK 0
+#define FRX_ERR_INVALID_ARG (-1)
+#define FRX_ERR_INFEASIBLE_GEOMETRY (-2) /* SE3GCOPTER::setup returning false, CPU.hpp:1118-1121 */
+#define FRX_ERR_CUDA (-3)
+#define FRX_ERR_CAPACITY (-4)            /* piece count / face count beyond a kernel limit */
+#define FRX_ERR_NOMEM (-5)
+
+/* Scalar arguments of SE3GCOPTER::setup, CPU.hpp:1076-1092 (same order, same meaning). */
+typedef struct frx_params {
+    double rho;            /* rh: time-regularisation weight; > 0 selects soft total time */
+    double total_t;        /* st: fixed total time when rho <= 0 */
+    double grid_res;       /* gridRes (INFINITY from the only caller, MinCoPlan_CPU.cpp:117) */
+    int itg_spaces;        /* itgSpaces = QdIntervals: quadrature intervals per piece */
+    int c2_diffeo;         /* c2diffeo */
+    double horiz_half_len; /* horiHalfLen */
+    double vert_half_len;  /* vertHalfLen */
+    double safe_margin;    /* margin */
+    double v_max;          /* vm */
+    double thr_acc_min;    /* minThrAcc */
+    double thr_acc_max;    /* maxThrAcc */
+    double body_rate_max;  /* bodyRateMax */
+    double grav_acc;       /* g */
+    double chi[4];         /* w: penalty weights (P, V, T, B) */
+} frx_params;
+
+/* One candidate trajectory = the remaining arguments of SE3GCOPTER::setup. */
+typedef struct frx_problem {
+    double ini[9];       /* iniState 3x3 column-major [p v a] */
+    double fin[9];       /* finState */
+    int n_poly;          /* cfgPolyHs.size() */
+    const int *face_off; /* n_poly + 1 offsets (in faces) */
+    const double *faces; /* 6 * face_off[n_poly] doubles */
+    /* Optional V-polytope override (2*n_poly - 1 polytopes in the reference's "origin + edge"
+     * form, CPU.hpp:1049: column 0 = v0, column k = v_k - v0).  NULL = enumerate from the
+     * half-spaces (replaces SE3GCOPTER::extractVs, CPU.hpp:1031-1074). */
+    const int *vert_off;  /* 2*n_poly offsets (in vertices), or NULL */
+    const double *verts;  /* 3 * vert_off[2*n_poly-1] doubles, or NULL */
+    frx_params params;
+} frx_problem;
+
+typedef struct frx_batch frx_batch; /* opaque: device + pinned memory for a batch of problems */
+
+/* --- construction: replaces SE3GCOPTER::setup (CPU.hpp:1076) and cuda_computer::setup
+ *     (cc.cuh:120) for every problem of the batch.  Builds the integer tables intervals /
+ *     idxVs / idxHs / cons / dimFreeT / dimFreeP (CPU.hpp:1123-1152) on the host, uploads
+ *     everything once.  device_ordinal < 0 = current device. ------------------------------- */
+int frx_batch_create(const frx_problem *problems, int count, int device_ordinal, frx_batch **out);
+/* Replaces ~SE3GCOPTER / cuda_computer::kill_kernel (cc.cuh:138): nothing spins on the device,
+ * so this only frees memory. */
+void frx_batch_destroy(frx_batch *b);
+
+/* --- queries ----------------------------------------------------------------------------- */
+int frx_batch_count(const frx_batch *b);
+/* n = dimFreeT + dimFreeP (the L-BFGS dimension), pieces = fineN, CPU.hpp:1125-1152 */
+int frx_batch_dims(const frx_batch *b, int traj, int *n, int *pieces, int *dim_t, int *dim_p);
+/* Packed layout of all per-trajectory x / gradient vectors: off[count+1]. */
+int frx_batch_x_offsets(const frx_batch *b, int *off);
+/* Same for per-piece outputs (durations): off[count+1] (in pieces). */
+int frx_batch_piece_offsets(const frx_batch *b, int *off);
+/* Integer tables of one trajectory, bit-exact with CPU.hpp:1123-1152: intervals[n_poly],
+ * idx_hs[pieces], idx_vs[pieces-1], cons[pieces].  Any pointer may be NULL. */
+int frx_batch_tables(const frx_batch *b, int traj, int *intervals, int *idx_hs, int *idx_vs, int *cons);
+/* V-polytopes in use for one trajectory (enumerated or supplied): vert_off[2*n_poly],
+ * verts[3*vert_off[2*n_poly-1]].  Call with verts == NULL to get only the offsets. */
+int frx_batch_vpolys(const frx_batch *b, int traj, int *vert_off, double *verts);
+
+/* --- the hot path ------------------------------------------------------------------------ */
+/* Starting point of the reference's optimize(): setInitial + backwardT + backwardP
+ * (CPU.hpp:1237-1240) for every trajectory; x is the packed host array (x_offsets). */
+int frx_batch_initial_guess(frx_batch *b, double *x_host);
+
+/* One cost+gradient evaluation of SE3GCOPTER::objectiveFunc (CPU.hpp:961-1000) for every
+ * trajectory of the batch.  Host buffers: x (packed), cost[count], grad (packed).  Copies
+ * host->device, runs the kernels, copies back, synchronises. */
+int frx_batch_eval(frx_batch *b, const double *x_host, double *cost_host, double *grad_host);
+/* Same with device-resident buffers on the given CUDA stream (cudaStream_t passed as void*;
+ * NULL = the batch's own stream).  Asynchronous: no synchronisation is performed. */
+int frx_batch_eval_device(frx_batch *b, const double *x_dev, double *cost_dev, double *grad_dev, void *stream);
+/* Number of kernel launches issued by one frx_batch_eval_device call. */
+int frx_batch_eval_launches(const frx_batch *b);
+
+/* Signature-identical to lbfgs_evaluate_t (lbfgs.hpp:223-226) so that the reference's own
+ * lbfgs_optimize can drive the CUDA evaluator: instance = a frx_batch of ONE trajectory. */
+double frx_eval(void *instance, const double *x, double *g, const int n);
+
+/* Full solve: replaces SE3GCOPTER::optimize (CPU.hpp:1230-1268) for every trajectory: batched
+ * device-side L-BFGS (mem_size 128, past 3, g_epsilon 1e-16, min_step 1e-32, delta = rel_tol;
+ * CPU.hpp:1243-1247) from frx_batch_initial_guess.  Outputs (any may be NULL):
+ *   durations[sum pieces]          piece durations (piece_offsets)
+ *   coeffs[18 * sum pieces]        per piece 3x6 column-major, highest order first (CPU.hpp:561)
+ *   jerk_cost[count]               return value of optimize() (jerk energy only, CPU.hpp:1267)
+ *   final_cost[count]              penalised objective at the final iterate
+ *   lbfgs_status[count]            lbfgs_optimize return code (discarded by the reference)
+ *   iterations[count], evaluations[count]
+ *   x_final (packed)               final (tau, xi) */
+int frx_batch_optimize(frx_batch *b, double rel_tol, double *durations, double *coeffs, double *jerk_cost,
+                       double *final_cost, int *lbfgs_status, int *iterations, int *evaluations,
+                       double *x_final);
+
+/* Arg-min of final_cost over the trajectories of this batch (ties -> lowest index).
+ * Device-side reduction; the cross-GPU gather is the caller's (NCCL all-gather of 16 B/rank). */
+int frx_batch_argmin(frx_batch *b, int *best_traj, double *best_cost);
+
+/* Device-time (ms, CUDA events on the batch stream) of the last eval / optimize call. */
+double frx_batch_last_ms(const frx_batch *b);
+
+const char *frx_strerror(int status);
+const char *frx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRX_H_ */

@@ -1,0 +1,939 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is part of the product path; only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+//
+// CPU restatement (plain C++17, no Eigen) of the reference's MINCO / SE(3)-GCOPTER back end:
+//   CPU.hpp  = /root/reference/src/plan_manage/include/se3gcopter/se3gcopter_cpu.hpp
+//   traj.hpp = /root/reference/src/plan_manage/include/se3gcopter/trajectory.hpp
+// Each function cites the lines it follows.  Operation order follows the reference literally
+// (running-sum abscissa, face loop order, accumulation order gdC -> gdT -> pena, penalty order
+// P,V,T-,T+,B).  Small fixed-size reductions (3-vector dots, 3x3 products) are summed left to
+// right; real Eigen may associate them differently (last-bit effects only).
+//
+// Parity status: the reference cannot be built here with its real dependency (Eigen is not in
+// the image and is not vendored).  This restatement is pinned (a) by its own finite-difference
+// and analytic known-answer tests and (b) against the verbatim reference headers compiled over
+// the Eigen-API shim in oracle/eigen_shim (oracle/_ref/libfrx_ref.so) when /root/reference exists;
+// see oracle/README.md and DESIGN.md for what that does and does not prove.
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "lbfgs_rc.hpp"
+
+namespace frx_oracle {
+
+// ------------------------------------------------------------------------------------------
+// Banded system, traj.hpp:599-752.  Storage map (i - j + upperBw) * N + j  (traj.hpp:645).
+// RHS is N x 3, held row-major here (the reference's per-row updates are element-wise, so the
+// layout does not change any arithmetic).
+// ------------------------------------------------------------------------------------------
+struct Banded {
+    int N = 0, lbw = 0, ubw = 0;
+    std::vector<double> d;
+    void create(int n, int p, int q) {
+        N = n, lbw = p, ubw = q;
+        d.assign((size_t)N * (lbw + ubw + 1), 0.0);
+    }
+    void reset() { std::fill(d.begin(), d.end(), 0.0); }
+    double& at(int i, int j) { return d[(size_t)(i - j + ubw) * N + j]; }
+    const double& at(int i, int j) const { return d[(size_t)(i - j + ubw) * N + j]; }
+
+    // traj.hpp:655-687 — in-place LU without pivoting, skipping exact zeros.
+    void factorizeLU() {
+        for (int k = 0; k <= N - 2; k++) {
+            const int iM = std::min(k + lbw, N - 1);
+            double cVl = at(k, k);
+            for (int i = k + 1; i <= iM; i++)
+                if (at(i, k) != 0.0) at(i, k) /= cVl;
+            const int jM = std::min(k + ubw, N - 1);
+            for (int j = k + 1; j <= jM; j++) {
+                cVl = at(k, j);
+                if (cVl != 0.0)
+                    for (int i = k + 1; i <= iM; i++)
+                        if (at(i, k) != 0.0) at(i, j) -= at(i, k) * cVl;
+            }
+        }
+    }
+    // traj.hpp:692-719
+    void solve(double* b) const {
+        for (int j = 0; j <= N - 1; j++) {
+            const int iM = std::min(j + lbw, N - 1);
+            for (int i = j + 1; i <= iM; i++)
+                if (at(i, j) != 0.0)
+                    for (int c = 0; c < 3; c++) b[3 * i + c] -= at(i, j) * b[3 * j + c];
+        }
+        for (int j = N - 1; j >= 0; j--) {
+            for (int c = 0; c < 3; c++) b[3 * j + c] /= at(j, j);
+            const int iM = std::max(0, j - ubw);
+            for (int i = iM; i <= j - 1; i++)
+                if (at(i, j) != 0.0)
+                    for (int c = 0; c < 3; c++) b[3 * i + c] -= at(i, j) * b[3 * j + c];
+        }
+    }
+    // traj.hpp:724-751
+    void solveAdj(double* b) const {
+        for (int j = 0; j <= N - 1; j++) {
+            for (int c = 0; c < 3; c++) b[3 * j + c] /= at(j, j);
+            const int iM = std::min(j + ubw, N - 1);
+            for (int i = j + 1; i <= iM; i++)
+                if (at(j, i) != 0.0)
+                    for (int c = 0; c < 3; c++) b[3 * i + c] -= at(j, i) * b[3 * j + c];
+        }
+        for (int j = N - 1; j >= 0; j--) {
+            const int iM = std::max(0, j - lbw);
+            for (int i = iM; i <= j - 1; i++)
+                if (at(j, i) != 0.0)
+                    for (int c = 0; c < 3; c++) b[3 * i + c] -= at(j, i) * b[3 * j + c];
+        }
+    }
+};
+
+// small 3-vector helpers (left-to-right sums)
+static inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline double sq3(const double* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
+static inline void cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// 3x3 matrices are row-major M[r*3+c] in this file.
+
+// Half-space description of one polytope: F faces, each (nx,ny,nz,px,py,pz) = one column of the
+// reference's 6 x F matrix (Plan_CPU.cpp:101).
+struct HPoly {
+    std::vector<double> f;  // 6*F
+    int faces() const { return (int)f.size() / 6; }
+};
+// V-polytope in the reference's "origin + edge" form (CPU.hpp:1049): col 0 = v0, col k = v_k - v0.
+struct VPoly {
+    std::vector<double> v;  // 3*V, column k at v[3k..3k+2]
+    int cols() const { return (int)v.size() / 3; }
+};
+
+struct PenaltyParams {
+    double ellipsoid[3];
+    double safeMargin, vMax, thrAccMin, thrAccMax, bdrMax, gAcc;
+    double chi[4];
+};
+
+// ------------------------------------------------------------------------------------------
+// MINCO_S3, CPU.hpp:37-565.  b (coefficients) and gdC are 6N x 3 row-major.
+// ------------------------------------------------------------------------------------------
+struct MincoS3 {
+    int N = 0;
+    double headPVA[9], tailPVA[9];  // column-major 3x3: col 0 = p, col 1 = v, col 2 = a
+    std::vector<double> T1, T2, T3, T4, T5;
+    Banded A;
+    std::vector<double> b, gdC;
+
+    // CPU.hpp:411-423
+    void reset(const double* head, const double* tail, int pieceNum) {
+        N = pieceNum;
+        std::memcpy(headPVA, head, sizeof(headPVA));
+        std::memcpy(tailPVA, tail, sizeof(tailPVA));
+        T1.assign(N, 0.);
+        A.create(6 * N, 6, 6);
+        b.assign((size_t)6 * N * 3, 0.);
+        gdC.assign((size_t)6 * N * 3, 0.);
+    }
+    double* row(std::vector<double>& m, int r) { return &m[(size_t)3 * r]; }
+    const double* row(const std::vector<double>& m, int r) const { return &m[(size_t)3 * r]; }
+
+    // CPU.hpp:425-505.  inPs: 3 x (N-1) column-major; ts: N.
+    void generate(const double* inPs, const double* ts) {
+        T1.assign(ts, ts + N);
+        T2.resize(N), T3.resize(N), T4.resize(N), T5.resize(N);
+        for (int i = 0; i < N; i++) {
+            T2[i] = T1[i] * T1[i];
+            T3[i] = T2[i] * T1[i];
+            T4[i] = T2[i] * T2[i];
+            T5[i] = T4[i] * T1[i];
+        }
+        A.reset();
+        std::fill(b.begin(), b.end(), 0.0);
+        A.at(0, 0) = 1.0;
+        A.at(1, 1) = 1.0;
+        A.at(2, 2) = 2.0;
+        for (int c = 0; c < 3; c++) {
+            b[0 + c] = headPVA[0 + c];
+            b[3 + c] = headPVA[3 + c];
+            b[6 + c] = headPVA[6 + c];
+        }
+        for (int i = 0; i < N - 1; i++) {
+            const int r = 6 * i;
+            A.at(r + 3, r + 3) = 6.0;
+            A.at(r + 3, r + 4) = 24.0 * T1[i];
+            A.at(r + 3, r + 5) = 60.0 * T2[i];
+            A.at(r + 3, r + 9) = -6.0;
+            A.at(r + 4, r + 4) = 24.0;
+            A.at(r + 4, r + 5) = 120.0 * T1[i];
+            A.at(r + 4, r + 10) = -24.0;
+            A.at(r + 5, r) = 1.0;
+            A.at(r + 5, r + 1) = T1[i];
+            A.at(r + 5, r + 2) = T2[i];
+            A.at(r + 5, r + 3) = T3[i];
+            A.at(r + 5, r + 4) = T4[i];
+            A.at(r + 5, r + 5) = T5[i];
+            A.at(r + 6, r) = 1.0;
+            A.at(r + 6, r + 1) = T1[i];
+            A.at(r + 6, r + 2) = T2[i];
+            A.at(r + 6, r + 3) = T3[i];
+            A.at(r + 6, r + 4) = T4[i];
+            A.at(r + 6, r + 5) = T5[i];
+            A.at(r + 6, r + 6) = -1.0;
+            A.at(r + 7, r + 1) = 1.0;
+            A.at(r + 7, r + 2) = 2 * T1[i];
+            A.at(r + 7, r + 3) = 3 * T2[i];
+            A.at(r + 7, r + 4) = 4 * T3[i];
+            A.at(r + 7, r + 5) = 5 * T4[i];
+            A.at(r + 7, r + 7) = -1.0;
+            A.at(r + 8, r + 2) = 2.0;
+            A.at(r + 8, r + 3) = 6 * T1[i];
+            A.at(r + 8, r + 4) = 12 * T2[i];
+            A.at(r + 8, r + 5) = 20 * T3[i];
+            A.at(r + 8, r + 8) = -2.0;
+            for (int c = 0; c < 3; c++) b[(size_t)3 * (r + 5) + c] = inPs[3 * i + c];
+        }
+        const int e = 6 * N;
+        const int l = N - 1;
+        A.at(e - 3, e - 6) = 1.0;
+        A.at(e - 3, e - 5) = T1[l];
+        A.at(e - 3, e - 4) = T2[l];
+        A.at(e - 3, e - 3) = T3[l];
+        A.at(e - 3, e - 2) = T4[l];
+        A.at(e - 3, e - 1) = T5[l];
+        A.at(e - 2, e - 5) = 1.0;
+        A.at(e - 2, e - 4) = 2 * T1[l];
+        A.at(e - 2, e - 3) = 3 * T2[l];
+        A.at(e - 2, e - 2) = 4 * T3[l];
+        A.at(e - 2, e - 1) = 5 * T4[l];
+        A.at(e - 1, e - 4) = 2;
+        A.at(e - 1, e - 3) = 6 * T1[l];
+        A.at(e - 1, e - 2) = 12 * T2[l];
+        A.at(e - 1, e - 1) = 20 * T3[l];
+        for (int c = 0; c < 3; c++) {
+            b[(size_t)3 * (e - 3) + c] = tailPVA[0 + c];
+            b[(size_t)3 * (e - 2) + c] = tailPVA[3 + c];
+            b[(size_t)3 * (e - 1) + c] = tailPVA[6 + c];
+        }
+        A.factorizeLU();
+        A.solve(b.data());
+    }
+
+    // CPU.hpp:507-520
+    double getTrajJerkCost() const {
+        double objective = 0.0;
+        for (int i = 0; i < N; i++) {
+            const double *c3 = row(b, 6 * i + 3), *c4 = row(b, 6 * i + 4), *c5 = row(b, 6 * i + 5);
+            objective += 36.0 * sq3(c3) * T1[i] + 144.0 * dot3(c4, c3) * T2[i] + 192.0 * sq3(c4) * T3[i] +
+                         240.0 * dot3(c5, c3) * T3[i] + 720.0 * dot3(c5, c4) * T4[i] + 720.0 * sq3(c5) * T5[i];
+        }
+        return objective;
+    }
+    // CPU.hpp:65-77
+    void addGradJbyT(double* gdT) const {
+        for (int i = 0; i < N; i++) {
+            const double *c3 = row(b, 6 * i + 3), *c4 = row(b, 6 * i + 4), *c5 = row(b, 6 * i + 5);
+            gdT[i] += 36.0 * sq3(c3) + 288.0 * dot3(c4, c3) * T1[i] + 576.0 * sq3(c4) * T2[i] +
+                      720.0 * dot3(c5, c3) * T2[i] + 2880.0 * dot3(c5, c4) * T3[i] + 3600.0 * sq3(c5) * T4[i];
+        }
+    }
+    // CPU.hpp:80-95
+    void addGradJbyC(std::vector<double>& g) const {
+        for (int i = 0; i < N; i++) {
+            const double *c3 = row(b, 6 * i + 3), *c4 = row(b, 6 * i + 4), *c5 = row(b, 6 * i + 5);
+            double *g3 = &g[(size_t)3 * (6 * i + 3)], *g4 = &g[(size_t)3 * (6 * i + 4)], *g5 = &g[(size_t)3 * (6 * i + 5)];
+            for (int c = 0; c < 3; c++) {
+                g5[c] += 240.0 * c3[c] * T3[i] + 720.0 * c4[c] * T4[i] + 1440.0 * c5[c] * T5[i];
+                g4[c] += 144.0 * c3[c] * T2[i] + 384.0 * c4[c] * T3[i] + 720.0 * c5[c] * T4[i];
+                g3[c] += 72.0 * c3[c] * T1[i] + 144.0 * c4[c] * T2[i] + 240.0 * c5[c] * T3[i];
+            }
+        }
+    }
+    // CPU.hpp:104-151.  adj = lambda (6N x 3 row-major).
+    void addPropCtoT(const std::vector<double>& adj, double* gdT) const {
+        double negVel[3], negAcc[3], negJer[3], negSnp[3], negCrk[3];
+        for (int i = 0; i < N - 1; i++) {
+            const double *c1 = row(b, 6 * i + 1), *c2 = row(b, 6 * i + 2), *c3 = row(b, 6 * i + 3),
+                         *c4 = row(b, 6 * i + 4), *c5 = row(b, 6 * i + 5);
+            for (int c = 0; c < 3; c++) {
+                negVel[c] = -(c1[c] + 2.0 * T1[i] * c2[c] + 3.0 * T2[i] * c3[c] + 4.0 * T3[i] * c4[c] + 5.0 * T4[i] * c5[c]);
+                negAcc[c] = -(2.0 * c2[c] + 6.0 * T1[i] * c3[c] + 12.0 * T2[i] * c4[c] + 20.0 * T3[i] * c5[c]);
+                negJer[c] = -(6.0 * c3[c] + 24.0 * T1[i] * c4[c] + 60.0 * T2[i] * c5[c]);
+                negSnp[c] = -(24.0 * c4[c] + 120.0 * T1[i] * c5[c]);
+                negCrk[c] = -120.0 * c5[c];
+            }
+            const double* B1[6] = {negSnp, negCrk, negVel, negVel, negAcc, negJer};
+            // cwiseProduct(...).sum() over a 6x3 block, column-major traversal
+            double s = 0.0;
+            for (int c = 0; c < 3; c++)
+                for (int r = 0; r < 6; r++) s += B1[r][c] * adj[(size_t)3 * (6 * i + 3 + r) + c];
+            gdT[i] += s;
+        }
+        const int l = N - 1;
+        const double *c1 = row(b, 6 * N - 5), *c2 = row(b, 6 * N - 4), *c3 = row(b, 6 * N - 3),
+                     *c4 = row(b, 6 * N - 2), *c5 = row(b, 6 * N - 1);
+        for (int c = 0; c < 3; c++) {
+            negVel[c] = -(c1[c] + 2.0 * T1[l] * c2[c] + 3.0 * T2[l] * c3[c] + 4.0 * T3[l] * c4[c] + 5.0 * T4[l] * c5[c]);
+            negAcc[c] = -(2.0 * c2[c] + 6.0 * T1[l] * c3[c] + 12.0 * T2[l] * c4[c] + 20.0 * T3[l] * c5[c]);
+            negJer[c] = -(6.0 * c3[c] + 24.0 * T1[l] * c4[c] + 60.0 * T2[l] * c5[c]);
+        }
+        const double* B2[3] = {negVel, negAcc, negJer};
+        double s = 0.0;
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 3; r++) s += B2[r][c] * adj[(size_t)3 * (6 * N - 3 + r) + c];
+        gdT[l] += s;
+    }
+    // CPU.hpp:154-161.  gdInP: 3 x (N-1) column-major.
+    void addPropCtoP(const std::vector<double>& adj, double* gdInP) const {
+        for (int i = 0; i < N - 1; i++)
+            for (int c = 0; c < 3; c++) gdInP[3 * i + c] += adj[(size_t)3 * (6 * i + 5) + c];
+    }
+
+    // CPU.hpp:163-185.  G row-major 3x3.
+    static void normalizeFDF(const double* x, double* xNor, double* G) {
+        const double a = x[0], bb = x[1], c = x[2];
+        const double aSqr = a * a, bSqr = bb * bb, cSqr = c * c;
+        const double ab = a * bb, bc = bb * c, ca = c * a;
+        const double xSqrNorm = aSqr + bSqr + cSqr;
+        const double xNorm = std::sqrt(xSqrNorm);
+        const double den = xSqrNorm * xNorm;
+        xNor[0] = a / xNorm, xNor[1] = bb / xNorm, xNor[2] = c / xNorm;
+        G[0] = bSqr + cSqr, G[1] = -ab, G[2] = -ca;
+        G[3] = -ab, G[4] = aSqr + cSqr, G[5] = -bc;
+        G[6] = -ca, G[7] = -bc, G[8] = aSqr + bSqr;
+        for (int i = 0; i < 9; i++) G[i] /= den;
+    }
+
+    // CPU.hpp:188-408.  cons[N] integration intervals, idxHs[N] owning polytope.
+    void addTimeIntPenalty(const int* cons, const int* idxHs, const std::vector<HPoly>& cfgHs,
+                           const PenaltyParams& P, double& cost, double* gdT, std::vector<double>& gC) const {
+        double pena = 0.0;
+        const double vMaxSqr = P.vMax * P.vMax;
+        const double thrAccMinSqr = P.thrAccMin * P.thrAccMin;
+        const double thrAccMaxSqr = P.thrAccMax * P.thrAccMax;
+        const double bdrMaxSqr = P.bdrMax * P.bdrMax;
+        const double* ell = P.ellipsoid;
+        const double* ci = P.chi;
+
+        for (int i = 0; i < N; i++) {
+            const double* c = row(b, 6 * i);  // 6x3 block, c[3*k+d]
+            double* gc = &gC[(size_t)18 * i];
+            const double step = T1[i] / cons[i];
+            double s1 = 0.0;
+            const int innerLoop = cons[i] + 1;
+            for (int j = 0; j < innerLoop; j++) {
+                const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                const double beta0[6] = {1.0, s1, s2, s3, s4, s5};
+                const double beta1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+                const double beta2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
+                const double beta3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
+                const double beta4[6] = {0.0, 0.0, 0.0, 0.0, 24.0, 120.0 * s1};
+                const double alpha = 1.0 / cons[i] * j;
+                double pos[3], vel[3], acc[3], jer[3], sna[3];
+                for (int d = 0; d < 3; d++) {
+                    double p = 0, v = 0, a = 0, jj = 0, sn = 0;
+                    for (int k = 0; k < 6; k++) {
+                        p += c[3 * k + d] * beta0[k];
+                        v += c[3 * k + d] * beta1[k];
+                        a += c[3 * k + d] * beta2[k];
+                        jj += c[3 * k + d] * beta3[k];
+                        sn += c[3 * k + d] * beta4[k];
+                    }
+                    pos[d] = p, vel[d] = v, acc[d] = a, jer[d] = jj, sna[d] = sn;
+                }
+                double h[3] = {acc[0], acc[1], acc[2] + P.gAcc};
+                double zB[3], dzB[9];
+                normalizeFDF(h, zB, dzB);
+                const double czB[3] = {0.0, zB[2], -zB[1]};
+                double cdzB[9] = {0, 0, 0, dzB[6], dzB[7], dzB[8], -dzB[3], -dzB[4], -dzB[5]};
+                double yB[3], dnczB[9];
+                normalizeFDF(czB, yB, dnczB);
+                double xB[3];
+                cross3(yB, zB, xB);
+                double dyB[9];
+                for (int r = 0; r < 3; r++)
+                    for (int cc = 0; cc < 3; cc++)
+                        dyB[3 * r + cc] = dnczB[3 * r + 0] * cdzB[0 + cc] + dnczB[3 * r + 1] * cdzB[3 + cc] + dnczB[3 * r + 2] * cdzB[6 + cc];
+                double dxB[9];
+                for (int m = 0; m < 3; m++) {
+                    const double dy[3] = {dyB[m], dyB[3 + m], dyB[6 + m]};
+                    const double dz[3] = {dzB[m], dzB[3 + m], dzB[6 + m]};
+                    double t0[3], t1[3];
+                    cross3(dy, zB, t0);
+                    cross3(yB, dz, t1);
+                    for (int r = 0; r < 3; r++) dxB[3 * r + m] = t0[r] + t1[r];
+                }
+                // rotM = [xB yB zB] (columns)
+                const double rotM[9] = {xB[0], yB[0], zB[0], xB[1], yB[1], zB[1], xB[2], yB[2], zB[2]};
+                // gradSdTxyz columns: dxB*jer, dyB*jer, dzB*jer
+                double gradSdTxyz[9];
+                for (int r = 0; r < 3; r++) {
+                    gradSdTxyz[3 * r + 0] = dxB[3 * r] * jer[0] + dxB[3 * r + 1] * jer[1] + dxB[3 * r + 2] * jer[2];
+                    gradSdTxyz[3 * r + 1] = dyB[3 * r] * jer[0] + dyB[3 * r + 1] * jer[1] + dyB[3 * r + 2] * jer[2];
+                    gradSdTxyz[3 * r + 2] = dzB[3 * r] * jer[0] + dzB[3 * r + 1] * jer[1] + dzB[3 * r + 2] * jer[2];
+                }
+                const double fThr = std::sqrt(sq3(h));
+                const double dfThr[3] = {h[0] / fThr, h[1] / fThr, h[2] / fThr};
+                const double sqrMagThr = fThr * fThr;
+                const double dSqrMagThr[3] = {2 * h[0], 2 * h[1], 2 * h[2]};
+                double rotTrDotJer[3];
+                for (int r = 0; r < 3; r++) rotTrDotJer[r] = rotM[0 + r] * jer[0] + rotM[3 + r] * jer[1] + rotM[6 + r] * jer[2];
+                const double bdr[3] = {rotTrDotJer[0] / fThr, rotTrDotJer[1] / fThr, rotTrDotJer[2] / fThr};
+                const double xyBdr[3] = {-bdr[1], bdr[0], 0.0};
+                const double sqrMagBdr = sq3(xyBdr);
+                // dBdr = -rotTrDotJer*dfThr^T/(fThr^2) - rotM^T*(dxB*r0 + dyB*r1 + dzB*r2)/fThr
+                double comb[9], dBdr[9];
+                for (int q = 0; q < 9; q++) comb[q] = dxB[q] * rotTrDotJer[0] + dyB[q] * rotTrDotJer[1] + dzB[q] * rotTrDotJer[2];
+                for (int r = 0; r < 3; r++)
+                    for (int cc = 0; cc < 3; cc++) {
+                        const double first = (-rotTrDotJer[r]) * dfThr[cc] / (fThr * fThr);
+                        const double prod = rotM[0 + r] * comb[0 + cc] + rotM[3 + r] * comb[3 + cc] + rotM[6 + r] * comb[6 + cc];
+                        dBdr[3 * r + cc] = first - prod / fThr;
+                    }
+                // dxyBdr rows: -dBdr.row(1), dBdr.row(0), 0
+                double dSqrMagBdr[3], dJerSqrMagBdr[3];
+                for (int cc = 0; cc < 3; cc++)
+                    dSqrMagBdr[cc] = 2.0 * xyBdr[0] * (-dBdr[3 + cc]) + 2.0 * xyBdr[1] * dBdr[0 + cc] + 2.0 * xyBdr[2] * 0.0;
+                // dJerBdr = rotM^T / fThr ; dJerxyBdr rows: -row1, row0, 0
+                for (int cc = 0; cc < 3; cc++) {
+                    const double r0 = rotM[3 * cc + 0] / fThr;  // (rotM^T)(0,cc)
+                    const double r1 = rotM[3 * cc + 1] / fThr;  // (rotM^T)(1,cc)
+                    dJerSqrMagBdr[cc] = 2.0 * xyBdr[0] * (-r1) + 2.0 * xyBdr[1] * r0 + 2.0 * xyBdr[2] * 0.0;
+                }
+
+                const double violaVel = sq3(vel) - vMaxSqr;
+                const double violaThrl = thrAccMinSqr - sqrMagThr;
+                const double violaThrh = sqrMagThr - thrAccMaxSqr;
+                const double violaBdr = sqrMagBdr - bdrMaxSqr;
+                const double omg = (j == 0 || j == innerLoop - 1) ? 0.5 : 1.0;
+
+                const HPoly& hp = cfgHs[idxHs[i]];
+                const int K = hp.faces();
+                for (int k = 0; k < K; k++) {
+                    const double* on = &hp.f[(size_t)6 * k];
+                    const double* pt = on + 3;
+                    // gradSdT = gradSdTxyz^T * n
+                    double gradSdT[3];
+                    for (int m = 0; m < 3; m++) gradSdT[m] = gradSdTxyz[0 + m] * on[0] + gradSdTxyz[3 + m] * on[1] + gradSdTxyz[6 + m] * on[2];
+                    const double outerNormaldVel = dot3(on, vel);
+                    // eNormGd = (rotM^T n) .* ellipsoid
+                    double eNormGd[3];
+                    for (int m = 0; m < 3; m++) eNormGd[m] = (rotM[0 + m] * on[0] + rotM[3 + m] * on[1] + rotM[6 + m] * on[2]) * ell[m];
+                    const double eNorm = std::sqrt(sq3(eNormGd));
+                    for (int m = 0; m < 3; m++) eNormGd[m] /= eNorm;
+                    const double dp[3] = {pos[0] - pt[0], pos[1] - pt[1], pos[2] - pt[2]};
+                    double signedDist = dot3(on, dp) + eNorm;
+                    for (int m = 0; m < 3; m++) eNormGd[m] *= ell[m];
+                    signedDist += P.safeMargin;
+                    if (signedDist > 0) {
+                        const double signedDistSqr = signedDist * signedDist;
+                        const double signedDistCub = signedDist * signedDistSqr;
+                        // gradSdC = beta0 n^T + (beta2 n^T) dxB e0 + (beta2 n^T) dyB e1 + (beta2 n^T) dzB e2
+                        const double fac = omg * step * ci[0] * 3.0 * signedDistSqr;
+                        for (int r = 0; r < 6; r++)
+                            for (int cc = 0; cc < 3; cc++) {
+                                const double gx = (beta2[r] * on[0]) * dxB[0 + cc] + (beta2[r] * on[1]) * dxB[3 + cc] + (beta2[r] * on[2]) * dxB[6 + cc];
+                                const double gy = (beta2[r] * on[0]) * dyB[0 + cc] + (beta2[r] * on[1]) * dyB[3 + cc] + (beta2[r] * on[2]) * dyB[6 + cc];
+                                const double gz = (beta2[r] * on[0]) * dzB[0 + cc] + (beta2[r] * on[1]) * dzB[3 + cc] + (beta2[r] * on[2]) * dzB[6 + cc];
+                                const double gradSdC = beta0[r] * on[cc] + gx * eNormGd[0] + gy * eNormGd[1] + gz * eNormGd[2];
+                                gc[3 * r + cc] += fac * gradSdC;
+                            }
+                        const double gradSignedDt = alpha * (outerNormaldVel + gradSdT[0] * eNormGd[0] + gradSdT[1] * eNormGd[1] + gradSdT[2] * eNormGd[2]);
+                        gdT[i] += omg * ci[0] * (3.0 * signedDistSqr * gradSignedDt * step + signedDistCub / cons[i]);
+                        pena += omg * step * ci[0] * signedDistCub;
+                    }
+                }
+
+                if (violaVel > 0.0) {
+                    double pd = violaVel * violaVel;
+                    const double pn = pd * violaVel;
+                    pd *= 3.0;
+                    const double gradViolaVt = (2.0 * alpha * vel[0]) * acc[0] + (2.0 * alpha * vel[1]) * acc[1] + (2.0 * alpha * vel[2]) * acc[2];
+                    const double fac = omg * step * ci[1] * pd;
+                    for (int r = 0; r < 6; r++)
+                        for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (2.0 * beta1[r] * vel[cc]);
+                    gdT[i] += omg * (ci[1] * pd * gradViolaVt * step + ci[1] * pn / cons[i]);
+                    pena += omg * step * ci[1] * pn;
+                }
+                if (violaThrl > 0.0) {
+                    double pd = violaThrl * violaThrl;
+                    const double pn = pd * violaThrl;
+                    pd *= 3.0;
+                    const double gt = (-alpha * dSqrMagThr[0]) * jer[0] + (-alpha * dSqrMagThr[1]) * jer[1] + (-alpha * dSqrMagThr[2]) * jer[2];
+                    const double fac = omg * step * ci[2] * pd;
+                    for (int r = 0; r < 6; r++)
+                        for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (-beta2[r] * dSqrMagThr[cc]);
+                    gdT[i] += omg * (ci[2] * pd * gt * step + ci[2] * pn / cons[i]);
+                    pena += omg * step * ci[2] * pn;
+                }
+                if (violaThrh > 0.0) {
+                    double pd = violaThrh * violaThrh;
+                    const double pn = pd * violaThrh;
+                    pd *= 3.0;
+                    const double gt = (alpha * dSqrMagThr[0]) * jer[0] + (alpha * dSqrMagThr[1]) * jer[1] + (alpha * dSqrMagThr[2]) * jer[2];
+                    const double fac = omg * step * ci[2] * pd;
+                    for (int r = 0; r < 6; r++)
+                        for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (beta2[r] * dSqrMagThr[cc]);
+                    gdT[i] += omg * (ci[2] * pd * gt * step + ci[2] * pn / cons[i]);
+                    pena += omg * step * ci[2] * pn;
+                }
+                if (violaBdr > 0.0) {
+                    double pd = violaBdr * violaBdr;
+                    const double pn = pd * violaBdr;
+                    pd *= 3.0;
+                    const double gt = alpha * (dot3(dSqrMagBdr, jer) + dot3(dJerSqrMagBdr, sna));
+                    const double fac = omg * step * ci[3] * pd;
+                    for (int r = 0; r < 6; r++)
+                        for (int cc = 0; cc < 3; cc++)
+                            gc[3 * r + cc] += fac * (beta2[r] * dSqrMagBdr[cc] + beta3[r] * dJerSqrMagBdr[cc]);
+                    gdT[i] += omg * (ci[3] * pd * gt * step + ci[3] * pn / cons[i]);
+                    pena += omg * step * ci[3] * pn;
+                }
+                s1 += step;
+            }
+        }
+        cost += pena;
+    }
+
+    // CPU.hpp:523-553.  gdT[N], gdInPs 3 x (N-1) col-major.
+    void evalTrajCostGrad(const int* cons, const int* idxHs, const std::vector<HPoly>& cfgHs,
+                          const PenaltyParams& P, double& cost, double* gdT, double* gdInPs) {
+        std::fill(gdT, gdT + N, 0.0);
+        std::fill(gdInPs, gdInPs + 3 * (N - 1), 0.0);
+        std::fill(gdC.begin(), gdC.end(), 0.0);
+        cost = getTrajJerkCost();
+        addGradJbyT(gdT);
+        addGradJbyC(gdC);
+        addTimeIntPenalty(cons, idxHs, cfgHs, P, cost, gdT, gdC);
+        A.solveAdj(gdC.data());
+        addPropCtoT(gdC, gdT);
+        addPropCtoP(gdC, gdInPs);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// SE3GCOPTER, CPU.hpp:567-1269.  V-polytopes are an INPUT here (the reference derives them in
+// extractVs, CPU.hpp:1031-1074, via geoutils/sdlp/quickhull — see oracle/geometry_oracle.hpp).
+// ------------------------------------------------------------------------------------------
+struct Se3Gcopter {
+    bool c2dfm = true, softT = true;
+    double rho = 0, sumT = 1;
+    MincoS3 jerkOpt;
+    double iState[9], fState[9];
+    std::vector<VPoly> cfgVs;
+    std::vector<HPoly> cfgHs;
+    std::vector<double> gdInPs;
+    std::vector<int> intervals, idxVs, idxHs, cons;
+    int coarseN = 0, fineN = 0, dimFreeT = 0, dimFreeP = 0;
+    std::vector<double> coarseT, fineT, innerP;
+    PenaltyParams pen;
+    int n_evals = 0;
+    int last_status = 0, last_iters = 0;
+
+    // ---- diffeomorphisms -----------------------------------------------------------------
+    // CPU.hpp:626-676
+    static void forwardT(const double* t, int nt, std::vector<double>& vecT, bool soft, double sT, bool c2) {
+        if (soft) {
+            const int M = (int)vecT.size();
+            for (int i = 0; i < M; i++)
+                vecT[i] = c2 ? (t[i] > 0.0 ? ((0.5 * t[i] + 1.0) * t[i] + 1.0) : 1.0 / ((0.5 * t[i] - 1.0) * t[i] + 1.0))
+                             : std::exp(t[i]);
+        } else {
+            const int Ms1 = nt;
+            for (int i = 0; i < Ms1; i++)
+                vecT[i] = c2 ? (t[i] > 0.0 ? ((0.5 * t[i] + 1.0) * t[i] + 1.0) : 1.0 / ((0.5 * t[i] - 1.0) * t[i] + 1.0))
+                             : std::exp(t[i]);
+            vecT[Ms1] = 0.0;
+            double s = 0.0;
+            for (double v : vecT) s += v;
+            const double den = 1.0 + s;
+            for (double& v : vecT) v /= den;
+            s = 0.0;
+            for (double v : vecT) s += v;
+            vecT[Ms1] = 1.0 - s;
+            for (double& v : vecT) v *= sT;
+        }
+    }
+    // CPU.hpp:679-726
+    static void backwardT(const std::vector<double>& vecT, double* t, int nt, bool soft, bool c2) {
+        if (soft) {
+            const int M = (int)vecT.size();
+            for (int i = 0; i < M; i++)
+                t[i] = c2 ? (vecT[i] > 1.0 ? (std::sqrt(2.0 * vecT[i] - 1.0) - 1.0) : (1.0 - std::sqrt(2.0 / vecT[i] - 1.0)))
+                          : std::log(vecT[i]);
+        } else {
+            const int Ms1 = nt;
+            for (int i = 0; i < Ms1; i++) {
+                const double r = vecT[i] / vecT[Ms1];
+                t[i] = c2 ? (r > 1.0 ? (std::sqrt(2.0 * r - 1.0) - 1.0) : (1.0 - std::sqrt(2.0 / r - 1.0))) : std::log(r);
+            }
+        }
+    }
+    // CPU.hpp:729-747.  inP 3 x M col-major.
+    static void forwardP(const double* p, const std::vector<int>& idVs, const std::vector<VPoly>& polys,
+                         std::vector<double>& inP) {
+        const int M = (int)inP.size() / 3;
+        int j = 0;
+        for (int i = 0; i < M; i++) {
+            const VPoly& vp = polys[idVs[i]];
+            const int k = vp.cols() - 1;
+            double sn = 0.0;
+            for (int a = 0; a < k; a++) sn += p[j + a] * p[j + a];
+            const double sc = 2.0 / (1.0 + sn);
+            for (int d = 0; d < 3; d++) {
+                double acc = 0.0;
+                for (int a = 0; a < k; a++) {
+                    const double q = sc * p[j + a];
+                    acc += vp.v[3 * (a + 1) + d] * (q * q);
+                }
+                inP[3 * i + d] = acc + vp.v[d];
+            }
+            j += k;
+        }
+    }
+    // CPU.hpp:749-774 (objective of the tiny NLS in backwardP).  pobs: 3 x (n+2) col-major.
+    static double objectiveNLS(void* ptr, const double* x, double* grad, const int n) {
+        const double* pobs = (const double*)ptr;
+        double qnsqr = 0.0;
+        for (int a = 0; a < n; a++) qnsqr += x[a] * x[a];
+        const double qnsqrp1 = qnsqr + 1.0;
+        const double qnsqrp1sqr = qnsqrp1 * qnsqrp1;
+        std::vector<double> r(n), gdr(n);
+        for (int a = 0; a < n; a++) r[a] = 2.0 / qnsqrp1 * x[a];
+        double delta[3];
+        for (int d = 0; d < 3; d++) {
+            double acc = 0.0;
+            for (int a = 0; a < n; a++) acc += pobs[3 * (a + 2) + d] * (r[a] * r[a]);
+            delta[d] = acc + pobs[3 * 1 + d] - pobs[d];
+        }
+        const double cost = sq3(delta);
+        const double gradR3[3] = {2 * delta[0], 2 * delta[1], 2 * delta[2]};
+        for (int a = 0; a < n; a++) {
+            gdr[a] = pobs[3 * (a + 2)] * gradR3[0] + pobs[3 * (a + 2) + 1] * gradR3[1] + pobs[3 * (a + 2) + 2] * gradR3[2];
+            gdr[a] = gdr[a] * r[a] * 2.0;
+        }
+        double gdp = 0.0;
+        for (int a = 0; a < n; a++) gdp += gdr[a] * x[a];
+        for (int a = 0; a < n; a++) grad[a] = gdr[a] * 2.0 / qnsqrp1 - x[a] * 4.0 * gdp / qnsqrp1sqr;
+        return cost;
+    }
+    // CPU.hpp:777-813
+    static void backwardP(const std::vector<double>& inP, const std::vector<int>& idVs, const std::vector<VPoly>& polys,
+                          double* p) {
+        const int M = (int)inP.size() / 3;
+        int j = 0;
+        LbfgsParams nls;
+        nls.g_epsilon = FLT_EPSILON;
+        nls.max_iterations = 128;
+        for (int i = 0; i < M; i++) {
+            const VPoly& vp = polys[idVs[i]];
+            const int k = vp.cols() - 1;
+            for (int a = 0; a < k; a++) p[j + a] = 1.0 / (std::sqrt(k + 1.0) + 1.0);
+            std::vector<double> pobs(3 * (k + 2));
+            for (int d = 0; d < 3; d++) pobs[d] = inP[3 * i + d];
+            std::memcpy(&pobs[3], vp.v.data(), sizeof(double) * 3 * (k + 1));
+            double minSqrD;
+            lbfgs_minimize(k, p + j, &minSqrD, &Se3Gcopter::objectiveNLS, pobs.data(), nls);
+            j += k;
+        }
+    }
+    // CPU.hpp:816-894
+    static void addLayerTGrad(const double* t, int nt, std::vector<double>& gradT, bool soft, double sT, bool c2) {
+        if (soft) {
+            for (int i = 0; i < nt; i++) {
+                if (c2) {
+                    if (t[i] > 0)
+                        gradT[i] *= t[i] + 1.0;
+                    else {
+                        const double denSqrt = (0.5 * t[i] - 1.0) * t[i] + 1.0;
+                        gradT[i] *= (1.0 - t[i]) / (denSqrt * denSqrt);
+                    }
+                } else
+                    gradT[i] *= std::exp(t[i]);
+            }
+        } else {
+            const int Ms1 = nt;
+            std::vector<double> gFree(Ms1), dExpTau(Ms1), eTau(Ms1);
+            for (int i = 0; i < Ms1; i++) gFree[i] = sT * gradT[i];
+            const double gTail = sT * gradT[Ms1];
+            double expTauSum = 0.0, gFreeDotExpTau = 0.0;
+            if (c2) {
+                for (int i = 0; i < Ms1; i++) {
+                    double expTau;
+                    if (t[i] > 0) {
+                        expTau = (0.5 * t[i] + 1.0) * t[i] + 1.0;
+                        dExpTau[i] = t[i] + 1.0;
+                    } else {
+                        const double denSqrt = (0.5 * t[i] - 1.0) * t[i] + 1.0;
+                        expTau = 1.0 / denSqrt;
+                        dExpTau[i] = (1.0 - t[i]) / (denSqrt * denSqrt);
+                    }
+                    expTauSum += expTau;
+                    gFreeDotExpTau += expTau * gFree[i];
+                }
+            } else {
+                for (int i = 0; i < Ms1; i++) dExpTau[i] = std::exp(t[i]);
+                for (int i = 0; i < Ms1; i++) expTauSum += dExpTau[i];
+                for (int i = 0; i < Ms1; i++) gFreeDotExpTau += gFree[i] * dExpTau[i];
+            }
+            const double den = expTauSum + 1.0;
+            for (int i = 0; i < Ms1; i++)
+                gradT[i] = (gFree[i] - gTail) * dExpTau[i] / den - (gFreeDotExpTau - gTail * expTauSum) * dExpTau[i] / (den * den);
+            gradT[Ms1] = 0.0;
+        }
+    }
+    // CPU.hpp:897-928
+    static void addLayerPGrad(const double* p, const std::vector<int>& idVs, const std::vector<VPoly>& polys,
+                              const std::vector<double>& gradInPs, double* grad) {
+        const int M = (int)gradInPs.size() / 3;
+        int j = 0;
+        for (int i = 0; i < M; i++) {
+            const VPoly& vp = polys[idVs[i]];
+            const int k = vp.cols() - 1;
+            const double* q = p + j;
+            double qnsqr = 0.0;
+            for (int a = 0; a < k; a++) qnsqr += q[a] * q[a];
+            const double qnsqrp1 = qnsqr + 1.0;
+            const double qnsqrp1sqr = qnsqrp1 * qnsqrp1;
+            std::vector<double> gdr(k);
+            for (int a = 0; a < k; a++) {
+                const double r = 2.0 / qnsqrp1 * q[a];
+                const double* e = &vp.v[3 * (a + 1)];
+                double g = e[0] * gradInPs[3 * i] + e[1] * gradInPs[3 * i + 1] + e[2] * gradInPs[3 * i + 2];
+                gdr[a] = g * r * 2.0;
+            }
+            double gq = 0.0;
+            for (int a = 0; a < k; a++) gq += gdr[a] * q[a];
+            for (int a = 0; a < k; a++) grad[j + a] = gdr[a] * 2.0 / qnsqrp1 - q[a] * 4.0 * gq / qnsqrp1sqr;
+            j += k;
+        }
+    }
+    // CPU.hpp:930-944
+    static void splitToFineT(const std::vector<double>& cT, const std::vector<int>& intervs, std::vector<double>& fT) {
+        int offset = 0;
+        for (size_t i = 0; i < intervs.size(); i++) {
+            const int iv = intervs[i];
+            for (int a = 0; a < iv; a++) fT[offset + a] = cT[i] / iv;
+            offset += iv;
+        }
+    }
+    // CPU.hpp:946-959
+    static void mergeToCoarseGradT(const std::vector<int>& intervs, std::vector<double>& fineGdT) {
+        int offset = 0;
+        for (size_t i = 0; i < intervs.size(); i++) {
+            const int iv = intervs[i];
+            double s = 0.0;
+            for (int a = 0; a < iv; a++) s += fineGdT[offset + a];
+            fineGdT[i] = s / iv;
+            offset += iv;
+        }
+    }
+
+    // CPU.hpp:961-1000
+    static double objectiveFunc(void* ptrObj, const double* x, double* grad, const int /*n*/) {
+        Se3Gcopter& o = *(Se3Gcopter*)ptrObj;
+        o.n_evals++;
+        const int dimT = o.dimFreeT, dimP = o.dimFreeP;
+        const double* t = x;
+        const double* p = x + dimT;
+        std::vector<double> proxyGradT(o.fineN);
+        forwardT(t, dimT, o.coarseT, o.softT, o.sumT, o.c2dfm);
+        splitToFineT(o.coarseT, o.intervals, o.fineT);
+        forwardP(p, o.idxVs, o.cfgVs, o.innerP);
+        double cost;
+        o.jerkOpt.generate(o.innerP.data(), o.fineT.data());
+        o.jerkOpt.evalTrajCostGrad(o.cons.data(), o.idxHs.data(), o.cfgHs, o.pen, cost, proxyGradT.data(), o.gdInPs.data());
+        double sT = 0.0;
+        for (double v : o.coarseT) sT += v;
+        cost += o.rho * sT;
+        for (double& v : proxyGradT) v += o.rho;
+        mergeToCoarseGradT(o.intervals, proxyGradT);
+        addLayerTGrad(t, dimT, proxyGradT, o.softT, o.sumT, o.c2dfm);
+        addLayerPGrad(p, o.idxVs, o.cfgVs, o.gdInPs, grad + dimT);
+        for (int i = 0; i < dimT; i++) grad[i] = proxyGradT[i];
+        return cost;
+    }
+
+    // CPU.hpp:1003-1029
+    void gridMesh(double gridResolution) {
+        const int M = (int)intervals.size();
+        double lastP[3], curP[3] = {iState[0], iState[1], iState[2]};
+        auto centroid = [&](const VPoly& vp, double* out) {
+            const int k = vp.cols() - 1;
+            for (int d = 0; d < 3; d++) {
+                double s = 0.0;
+                for (int a = 0; a < k; a++) s += vp.v[3 * (a + 1) + d];
+                out[d] = s / (1.0 + k) + vp.v[d];
+            }
+        };
+        for (int i = 0; i < M - 1; i++) {
+            std::memcpy(lastP, curP, sizeof(curP));
+            centroid(cfgVs[2 * i + 1], curP);
+            const double dd[3] = {curP[0] - lastP[0], curP[1] - lastP[1], curP[2] - lastP[2]};
+            const int cur = (int)std::ceil(std::sqrt(sq3(dd)) / gridResolution);
+            intervals[i] = cur > 0 ? cur : 1;
+        }
+        std::memcpy(lastP, curP, sizeof(curP));
+        const double dd[3] = {fState[0] - lastP[0], fState[1] - lastP[1], fState[2] - lastP[2]};
+        const int cur = (int)std::ceil(std::sqrt(sq3(dd)) / gridResolution);
+        intervals[M - 1] = cur > 0 ? cur : 1;
+    }
+
+    // CPU.hpp:1076-1186, with cfgVs supplied (2*coarseN-1 V-polytopes, origin+edge form).
+    // hPolys: face normals are normalised here as at CPU.hpp:1116.
+    bool setup(double rh, double st, const double* iniState, const double* finState, const std::vector<HPoly>& cfgPolyHs,
+               const std::vector<VPoly>& vPolys, double gridRes, int itgSpaces, double horiHalfLen, double vertHalfLen,
+               double margin, double vm, double minThrAcc, double maxThrAcc, double bodyRateMax, double g,
+               const double* w, bool c2diffeo) {
+        c2dfm = c2diffeo;
+        softT = rh > 0;
+        if (softT) {
+            rho = rh;
+            sumT = 1.0;
+        } else {
+            rho = 0.0;
+            sumT = st;
+        }
+        std::memcpy(iState, iniState, sizeof(iState));
+        std::memcpy(fState, finState, sizeof(fState));
+        cfgHs = cfgPolyHs;
+        coarseN = (int)cfgHs.size();
+        for (auto& hp : cfgHs)
+            for (int k = 0; k < hp.faces(); k++) {
+                double* nn = &hp.f[(size_t)6 * k];
+                const double nrm = std::sqrt(sq3(nn));
+                nn[0] /= nrm, nn[1] /= nrm, nn[2] /= nrm;
+            }
+        cfgVs = vPolys;
+        if ((int)cfgVs.size() != 2 * coarseN - 1) return false;
+        intervals.assign(coarseN, 0);
+        gridMesh(gridRes);
+        fineN = 0;
+        for (int v : intervals) fineN += v;
+        cons.assign(fineN, itgSpaces);
+        idxVs.assign(fineN - 1, 0);
+        idxHs.assign(fineN, 0);
+        dimFreeT = softT ? coarseN : coarseN - 1;
+        dimFreeP = 0;
+        int offset = 0;
+        for (int i = 0; i < coarseN; i++) {
+            const int interval = intervals[i];
+            for (int j = 0; j < interval; j++) {
+                if (j < interval - 1) {
+                    idxVs[offset] = 2 * i;
+                    dimFreeP += cfgVs[2 * i].cols() - 1;
+                } else if (i < coarseN - 1) {
+                    idxVs[offset] = 2 * i + 1;
+                    dimFreeP += cfgVs[2 * i + 1].cols() - 1;
+                }
+                idxHs[offset] = i;
+                offset++;
+            }
+        }
+        for (int i = 0; i < 4; i++) pen.chi[i] = w[i];
+        pen.ellipsoid[0] = horiHalfLen, pen.ellipsoid[1] = horiHalfLen, pen.ellipsoid[2] = vertHalfLen;
+        pen.safeMargin = margin, pen.vMax = vm, pen.thrAccMin = minThrAcc, pen.thrAccMax = maxThrAcc;
+        pen.bdrMax = bodyRateMax, pen.gAcc = g;
+        // CPU.hpp:1166-1170 "legal initial speed": clamps the member copies only (dead store for
+        // everything but setInitial, which reads column 0 = position).  Reproduced, not fixed.
+        auto clampv = [&](double* S) {
+            const double tn = std::sqrt(sq3(S + 3));
+            const double sc = tn > pen.vMax ? (pen.vMax / tn) : 1.0;
+            S[3] *= sc, S[4] *= sc, S[5] *= sc;
+        };
+        clampv(iState);
+        clampv(fState);
+        coarseT.assign(coarseN, 0.);
+        fineT.assign(fineN, 0.);
+        innerP.assign((size_t)3 * (fineN - 1), 0.);
+        gdInPs.assign((size_t)3 * (fineN - 1), 0.);
+        jerkOpt.reset(iniState, finState, fineN);  // unclamped states, CPU.hpp:1180
+        return true;
+    }
+
+    // CPU.hpp:1188-1228
+    void setInitial(std::vector<double>& vecT, std::vector<double>& vecInP) const {
+        const double maxSpeedForAllocation = 10.0;
+        const int M = (int)vecT.size();
+        double lastP[3], curP[3] = {iState[0], iState[1], iState[2]}, delta[3];
+        int offset = 0;
+        const double spd = std::min(pen.vMax, maxSpeedForAllocation);
+        for (int i = 0; i < M - 1; i++) {
+            std::memcpy(lastP, curP, sizeof(curP));
+            const int interv = intervals[i];
+            const VPoly& vp = cfgVs[2 * i + 1];
+            const int k = vp.cols() - 1;
+            for (int d = 0; d < 3; d++) {
+                double s = 0.0;
+                for (int a = 0; a < k; a++) s += vp.v[3 * (a + 1) + d];
+                curP[d] = s / (1.0 + k) + vp.v[d];
+            }
+            for (int d = 0; d < 3; d++) delta[d] = curP[d] - lastP[d];
+            vecT[i] = std::sqrt(sq3(delta)) / spd;
+            for (int d = 0; d < 3; d++) delta[d] /= interv;
+            for (int j = 0; j < interv; j++) {
+                for (int d = 0; d < 3; d++) vecInP[3 * offset + d] = (j + 1) * delta[d] + lastP[d];
+                offset++;
+            }
+        }
+        const int interv = intervals[M - 1];
+        std::memcpy(lastP, curP, sizeof(curP));
+        for (int d = 0; d < 3; d++) delta[d] = fState[d] - lastP[d];
+        vecT[M - 1] = std::sqrt(sq3(delta)) / spd;
+        for (int d = 0; d < 3; d++) delta[d] /= interv;
+        for (int j = 0; j < interv - 1; j++) {
+            for (int d = 0; d < 3; d++) vecInP[3 * offset + d] = (j + 1) * delta[d] + lastP[d];
+            offset++;
+        }
+    }
+
+    int dim() const { return dimFreeT + dimFreeP; }
+
+    // The x the reference starts L-BFGS from: CPU.hpp:1237-1240.
+    void initialGuess(double* x) {
+        setInitial(coarseT, innerP);
+        backwardT(coarseT, x, dimFreeT, softT, c2dfm);
+        backwardP(innerP, idxVs, cfgVs, x + dimFreeT);
+    }
+
+    // CPU.hpp:1230-1268.  durations[fineN]; coeffs[fineN*18]: per piece a 3x6 column-major
+    // matrix, highest order first (CPU.hpp:561, traj.hpp:39).  Returns the jerk cost only.
+    double optimize(double relCostTol, double* durations, double* coeffs, double* x_final = nullptr,
+                    double* penalised_cost = nullptr) {
+        std::vector<double> x(dim());
+        initialGuess(x.data());
+        LbfgsParams lp;
+        lp.mem_size = 128;
+        lp.past = 3;
+        lp.g_epsilon = 1.0e-16;
+        lp.min_step = 1.0e-32;
+        lp.delta = relCostTol;
+        double minObjectivePenalty = 0.0;
+        int evals = 0;
+        last_status = lbfgs_minimize(dim(), x.data(), &minObjectivePenalty, &Se3Gcopter::objectiveFunc, this, lp,
+                                     &last_iters, &evals);
+        forwardT(x.data(), dimFreeT, coarseT, softT, sumT, c2dfm);
+        splitToFineT(coarseT, intervals, fineT);
+        forwardP(x.data() + dimFreeT, idxVs, cfgVs, innerP);
+        jerkOpt.generate(innerP.data(), fineT.data());
+        getTraj(durations, coeffs);
+        if (x_final) std::memcpy(x_final, x.data(), sizeof(double) * dim());
+        if (penalised_cost) *penalised_cost = minObjectivePenalty;
+        return jerkOpt.getTrajJerkCost();
+    }
+
+    // CPU.hpp:555-564: Piece(T_i, b.block<6,3>(6i,0)^T.rowwise().reverse()) -> 3x6, col-major.
+    void getTraj(double* durations, double* coeffs) const {
+        for (int i = 0; i < fineN; i++) {
+            durations[i] = jerkOpt.T1[i];
+            for (int col = 0; col < 6; col++)
+                for (int d = 0; d < 3; d++) coeffs[(size_t)18 * i + 3 * col + d] = jerkOpt.b[(size_t)3 * (6 * i + (5 - col)) + d];
+        }
+    }
+};
+
+}  // namespace frx_oracle
