@@ -142,6 +142,7 @@ def load_library():
         "frx_batch_eval": (ci, [vp, P(cd), P(cd), P(cd)]),
         "frx_batch_eval_device": (ci, [vp, vp, vp, vp, vp]),
         "frx_batch_eval_launches": (ci, [vp]),
+        "frx_batch_stream": (vp, [vp]),
         "frx_eval": (cd, [vp, P(cd), P(cd), ci]),
         "frx_batch_optimize": (ci, [vp, cd, P(cd), P(cd), P(cd), P(cd), P(ci), P(ci), P(ci), P(cd)]),
         "frx_batch_argmin": (ci, [vp, P(ci), P(cd)]),
@@ -153,6 +154,9 @@ def load_library():
         "frx_host_model": (ci, [P(FrxProblem), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(cd)]),
         "frx_host_vpolys": (ci, [P(FrxProblem), P(ci), P(cd)]),
         "frx_batch_solver_ticks": (ci, [vp]),
+        "frx_batch_profile_eval": (ci, [vp, vp, vp, vp, vp, ci, P(cd)]),
+        "frx_batch_penalty_launch": (ci, [vp, P(C.c_longlong)]),
+        "frx_measure_fp64_tflops": (cd, []),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -165,7 +169,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "frx_batch_create", "frx_batch_destroy", "frx_batch_count", "frx_batch_dims", "frx_batch_x_offsets",
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
-    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
+    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version",
 ]
 
@@ -292,6 +296,22 @@ class Batch:
         """Device-pointer evaluation on a CUDA stream (integers: data_ptr() / cuda_stream)."""
         _check(self.lib.frx_batch_eval_device(self.h, C.c_void_p(x_ptr), C.c_void_p(cost_ptr), C.c_void_p(grad_ptr),
                                               C.c_void_p(stream_ptr)), "frx_batch_eval_device")
+
+    def stream(self):
+        """cudaStream_t (as int) of the batch's own stream."""
+        return int(self.lib.frx_batch_stream(self.h) or 0)
+
+    def profile_eval(self, x_ptr, cost_ptr, grad_ptr, stream_ptr, reps):
+        """Average device ms of (minco_forward, penalty, minco_backward) over reps evaluations."""
+        ms = np.zeros(3)
+        _check(self.lib.frx_batch_profile_eval(self.h, C.c_void_p(x_ptr), C.c_void_p(cost_ptr), C.c_void_p(grad_ptr),
+                                               C.c_void_p(stream_ptr), reps, _dp(ms)), "frx_batch_profile_eval")
+        return ms
+
+    def penalty_launch(self):
+        out = (C.c_longlong * 6)()
+        _check(self.lib.frx_batch_penalty_launch(self.h, out), "penalty_launch")
+        return dict(zip(("samples_per_thread", "threads_per_piece", "pieces_per_cta", "cta_threads", "grid", "smem_bytes"), list(out)))
 
     def eval_launches(self):
         return self.lib.frx_batch_eval_launches(self.h)

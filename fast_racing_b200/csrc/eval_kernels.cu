@@ -737,4 +737,69 @@ cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd
     return cudaGetLastError();
 }
 
+
+// Per-kernel device times of `reps` evaluations: CUDA events on the launching stream around each
+// of the three kernels.  ms[3] = average duration of K1, K2, K3.
+cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms) {
+    cudaEvent_t ev[4];
+    for (auto& e : ev) cudaEventCreate(&e);
+    ms[0] = ms[1] = ms[2] = 0.0;
+    cudaError_t err = cudaSuccess;
+    for (int r = 0; r < reps && err == cudaSuccess; r++) {
+        cudaEventRecord(ev[0], st);
+        minco_forward_kernel<<<bv.B, 32, fwd_smem, st>>>(bv, x_dev);
+        cudaEventRecord(ev[1], st);
+        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
+        cudaEventRecord(ev[2], st);
+        minco_backward_kernel<<<bv.B, 32, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+        cudaEventRecord(ev[3], st);
+        err = cudaStreamSynchronize(st);
+        for (int k = 0; k < 3 && err == cudaSuccess; k++) {
+            float t = 0.f;
+            err = cudaEventElapsedTime(&t, ev[k], ev[k + 1]);
+            ms[k] += t / reps;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return err;
+}
+
+// fp64 FMA peak micro-benchmark: 8 independent DFMA chains per thread.
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c), a1 = fma(a1, m, c), a2 = fma(a2, m, c), a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c), a5 = fma(a5, m, c), a6 = fma(a6, m, c), a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+double measure_fp64_tflops() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int r = 0; r < 5; r++) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+        best = fmax(best, fl / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
 }  // namespace frx

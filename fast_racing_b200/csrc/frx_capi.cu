@@ -21,6 +21,9 @@ PenaltyLaunch plan_penalty(const BatchView& bv);
 cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);
 cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st);
+cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);
+double measure_fp64_tflops();
 }  // namespace frx
 
 using namespace frx;
@@ -342,11 +345,12 @@ int frx_batch_initial_guess(frx_batch* b, double* x_host) {
 }
 
 int frx_batch_eval_launches(const frx_batch* b) { return b ? 3 : FRX_ERR_INVALID_ARG; }
+void* frx_batch_stream(frx_batch* b) { return b ? (void*)b->stream : nullptr; }
 
 int frx_batch_eval_device(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream) {
     if (!b || !x_dev || !cost_dev || !grad_dev) return FRX_ERR_INVALID_ARG;
     CK(cudaSetDevice(b->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, st));
     return FRX_OK;
 }
@@ -380,6 +384,24 @@ double frx_eval(void* instance, const double* x, double* g, const int n) {
 }
 
 double frx_batch_last_ms(const frx_batch* b) { return b ? b->last_ms : -1.0; }
+
+// Average device time (ms) of each of the three evaluation kernels over `reps` evaluations at x_dev,
+// CUDA events on the given stream.  ms_out[3] = {minco_forward, penalty, minco_backward}.
+int frx_batch_profile_eval(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream, int reps,
+                           double* ms_out) {
+    if (!b || !x_dev || !cost_dev || !grad_dev || !ms_out || reps < 1) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(b->device));
+    CK(profile_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
+    return FRX_OK;
+}
+// Launch geometry of the penalty kernel: out[6] = {samples/thread, threads/piece, pieces/CTA, CTA threads, grid, smem bytes}
+int frx_batch_penalty_launch(const frx_batch* b, long long* out) {
+    if (!b || !out) return FRX_ERR_INVALID_ARG;
+    out[0] = b->pl.spt, out[1] = b->pl.tpp, out[2] = b->pl.ppc, out[3] = b->pl.threads, out[4] = b->pl.grid, out[5] = (long long)b->pl.smem;
+    return FRX_OK;
+}
+// Measured fp64 FMA peak (TFLOP/s) of the current device: the secondary roofline of this path.
+double frx_measure_fp64_tflops(void) { return measure_fp64_tflops(); }
 
 // Intermediate device quantities of the last evaluation (for component-level parity tests):
 // T[pieces], q[3*pieces] (last slot unused), c[18*pieces], gdC_lambda[18*pieces], pen[pieces], energy[pieces], gdT[pieces]

@@ -102,8 +102,10 @@ int frx_batch_initial_guess(frx_batch *b, double *x_host);
  * host->device, runs the kernels, copies back, synchronises. */
 int frx_batch_eval(frx_batch *b, const double *x_host, double *cost_host, double *grad_host);
 /* Same with device-resident buffers on the given CUDA stream (cudaStream_t passed as void*;
- * NULL = the batch's own stream).  Asynchronous: no synchronisation is performed. */
+ * NULL = the CUDA default stream, as everywhere in CUDA).  Asynchronous: no synchronisation. */
 int frx_batch_eval_device(frx_batch *b, const double *x_dev, double *cost_dev, double *grad_dev, void *stream);
+/* The batch's own (non-blocking) stream, on which frx_batch_eval / frx_batch_optimize run. */
+void *frx_batch_stream(frx_batch *b);
 /* Number of kernel launches issued by one frx_batch_eval_device call. */
 int frx_batch_eval_launches(const frx_batch *b);
 

@@ -51,6 +51,8 @@ def lib():
         L.fro_penalty_only.argtypes = [vp, P(cd), P(cd), P(cd)]
         L.fro_optimize.restype = cd
         L.fro_optimize.argtypes = [vp, cd, P(cd), P(cd), P(cd), P(cd), P(ci), P(ci), P(ci)]
+        L.fro_optimize_from.restype = cd
+        L.fro_optimize_from.argtypes = [vp, P(cd), cd]
         L.fro_time_evals.restype = cd
         L.fro_time_evals.argtypes = [vp, P(cd), ci]
         L.fro_time_evals_mt.restype = cd

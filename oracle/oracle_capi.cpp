@@ -106,6 +106,16 @@ double fro_optimize(void* hv, double rel_tol, double* durations, double* coeffs,
     return j;
 }
 
+// L-BFGS with the reference's optimize() parameters (CPU.hpp:1243-1247) from an arbitrary start x (in/out).
+double fro_optimize_from(void* hv, double* x, double rel_tol) {
+    auto& o = ((OracleHandle*)hv)->opt;
+    LbfgsParams lp;
+    lp.mem_size = 128, lp.past = 3, lp.g_epsilon = 1.0e-16, lp.min_step = 1.0e-32, lp.delta = rel_tol;
+    double fx = 0.0;
+    o.last_status = lbfgs_minimize(o.dim(), x, &fx, &Se3Gcopter::objectiveFunc, &o, lp, &o.last_iters, nullptr);
+    return fx;
+}
+
 // ---- timing helpers for bench.py's cpu_baseline -------------------------------------------
 // Seconds for `reps` evaluations at fixed x on one core.
 double fro_time_evals(void* hv, const double* x, int reps) {

@@ -1,0 +1,76 @@
+"""Generates the committed golden fixtures tests/golden/*.npz.
+
+Run in the authoring container (where /root/reference exists):  python tests/golden/make_golden.py
+Each fixture holds one small problem (faces, V-polytopes, parameters), evaluation points, and the outputs of
+  * the CPU oracle (oracle/gcopter_oracle.hpp): cost, gradient, T, q, c, index tables, initial guess,
+  * the oracle's objective driven by the VERBATIM reference lbfgs.hpp (oracle/_ref/libref_lbfgs.so):
+    final x / cost / status — and the restated L-BFGS must reproduce them bit for bit,
+  * when oracle/_ref/libfrx_ref.so exists (verbatim se3gcopter_cpu.hpp over the Eigen-API shim): the
+    reference's own cost/gradient at the same points ("ref_cost", "ref_grad").
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from fast_racing_b200 import api, synth  # noqa: E402
+from oracle import binding as ob  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (problem factory, perturbation sigma)
+    "c1_small": (lambda: synth.make_problem(101, 8, 10, 12, chi=(0.0, 1.0e4, 1.0e4, 1.0e4), gates=(1, 3, 5, 7)), 0.05),
+    "sfc_small": (lambda: synth.make_problem(102, 6, 12, 8), 0.05),
+    "ragged_faces": (lambda: synth.make_problem(103, 5, np.array([8, 14, 6, 20, 9]), 10, gates=(2,)), 0.1),
+    "moderncity_small": (lambda: synth.make_problem(104, 7, 12, 16, params=api.MODERNCITY), 0.05),
+}
+
+
+def main():
+    R = ob.ref_lbfgs()
+    L = ob.lib()
+    for name, (factory, sigma) in CASES.items():
+        p = factory()
+        off, verts = api.host_vpolys(p)
+        pv = p.with_vpolys(off, verts)
+        o = ob.Oracle(pv)
+        x0 = o.initial_guess()
+        rng = np.random.default_rng(abs(hash(name)) % (2**31))
+        rng = np.random.default_rng(sum(map(ord, name)))
+        xs = np.stack([x0, x0 + sigma * rng.normal(size=x0.size), x0 + 3 * sigma * rng.normal(size=x0.size)])
+        costs, grads, Ts, qs, cs = [], [], [], [], []
+        for x in xs:
+            f, g = o.eval(x)
+            T, q, c = o.forward(x)
+            costs.append(f), grads.append(g), Ts.append(T), qs.append(q), cs.append(c)
+        tab = o.tables()
+        out = dict(ini=p.ini, fin=p.fin, face_off=p.face_off, faces=p.faces, vert_off=off, verts=verts,
+                   params_keys=np.array(sorted(k for k in p.params if k != "chi")),
+                   params_vals=np.array([float(p.params[k]) for k in sorted(p.params) if k != "chi"]),
+                   chi=np.array(p.params["chi"]), xs=xs, cost=np.array(costs), grad=np.stack(grads), T=np.stack(Ts),
+                   q=np.stack(qs), c=np.stack(cs), x0=x0, **{f"tab_{k}": v for k, v in tab.items()},
+                   dims=np.array([o.n, o.pieces, o.dim_t, o.dim_p]))
+        tol = p.params.get("rel_tol", 1e-5)
+        r = o.optimize(tol)
+        out.update(opt_x=r["x"], opt_final_cost=r["final_cost"], opt_jerk_cost=r["jerk_cost"], opt_status=r["status"],
+                   opt_iterations=r["iterations"], opt_evaluations=r["evaluations"], opt_durations=r["durations"],
+                   opt_coeffs=r["coeffs"], opt_rel_tol=tol)
+        if R is not None:
+            xr = x0.copy()
+            fr = C.c_double()
+            cb = ob.EVAL_T(lambda inst, x, g, n: L.fro_eval(o.h, x, g, n))
+            st = R.ref_lbfgs_optimize(o.n, xr.ctypes.data_as(C.POINTER(C.c_double)), C.byref(fr), cb, None, 128, 3, tol, 1e-16, 1e-32, 0)
+            assert st == r["status"] and fr.value == r["final_cost"] and np.array_equal(xr, r["x"]), \
+                f"{name}: restated L-BFGS deviates from the verbatim reference lbfgs.hpp"
+            out.update(reflbfgs_x=xr, reflbfgs_cost=fr.value, reflbfgs_status=st)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, "n", o.n, "cost", costs, "opt", r["final_cost"], r["status"], r["iterations"])
+        o.close()
+
+
+if __name__ == "__main__":
+    main()
