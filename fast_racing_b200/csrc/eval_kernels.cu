@@ -22,7 +22,8 @@ namespace frx {
 // ------------------------------------------------------------------------------------------------
 // Band storage used on the device: row-major, 16 doubles per row: slot (j - i + 6) for column j of
 // row i (13 diagonals, bandwidth 6/6 as trajectory.hpp:645 with N-major order swapped for coalesced
-// row access), slots 13..15 = the three right-hand sides (x,y,z).
+// row access), slot 13 = reciprocal of the U diagonal, slots 14..15 unused.  After the factorisation slots
+// 0..5 hold the multipliers l_{i,i-6..i-1}, 6 the diagonal of U, 7..12 its upper band.
 // ------------------------------------------------------------------------------------------------
 #define BW 16
 
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
         }
     }
     for (int i = lane; i < N * BW; i += 32) As[i] = 0.0;
+    for (int i = lane; i < 3 * N; i += 32) cs[i] = 0.0;
     __syncwarp();
     // ---- splitToFineT (CPU.hpp:930-944) + forwardP (CPU.hpp:729-747) ----
     for (int i = lane; i < M; i += 32) {
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
             A_(r + 8, r + 4) = 12 * T2;
             A_(r + 8, r + 5) = 20 * T3;
             A_(r + 8, r + 8) = -2.0;
-            As[(size_t)(r + 5) * BW + 13] = qx;
-            As[(size_t)(r + 5) * BW + 14] = qy;
-            As[(size_t)(r + 5) * BW + 15] = qz;
+            cs[3 * (r + 5) + 0] = qx;
+            cs[3 * (r + 5) + 1] = qy;
+            cs[3 * (r + 5) + 2] = qz;
         } else {
             // last piece: tail rows (CPU.hpp:481-499) and, by the same lane, the head rows (:437-442)
             const double T1 = Ti, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
@@ -155,70 +157,91 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
             A_(2, 2) = 2.0;
             const double* ht = bv.headtail + 18 * (size_t)b;
             for (int d = 0; d < 3; d++) {
-                As[0 * BW + 13 + d] = ht[0 + d];
-                As[1 * BW + 13 + d] = ht[3 + d];
-                As[2 * BW + 13 + d] = ht[6 + d];
-                As[(size_t)(e - 3) * BW + 13 + d] = ht[9 + 0 + d];
-                As[(size_t)(e - 2) * BW + 13 + d] = ht[9 + 3 + d];
-                As[(size_t)(e - 1) * BW + 13 + d] = ht[9 + 6 + d];
+                cs[0 + d] = ht[0 + d];
+                cs[3 + d] = ht[3 + d];
+                cs[6 + d] = ht[6 + d];
+                cs[3 * (e - 3) + d] = ht[9 + 0 + d];
+                cs[3 * (e - 2) + d] = ht[9 + 3 + d];
+                cs[3 * (e - 1) + d] = ht[9 + 6 + d];
             }
 #undef A_
         }
     }
     __syncwarp();
 
-    // ---- banded LU without pivoting (trajectory.hpp:655-687) fused with the forward substitution
-    //      of the three right-hand sides (:695-705).  Pivot k: the 6 rows below x (6 columns + 3 RHS)
-    //      = 54 updates, spread as 6 row groups x 5 lanes, <= 2 slots per lane.  The reference's
-    //      skip-exact-zero tests only skip arithmetic that leaves the data unchanged.
+    // ---- banded LU without pivoting (trajectory.hpp:655-687).  Pivot k updates the 6x6 block below /
+    //      right of it: 6 row groups x 3 lanes, 2 columns per lane.  One barrier per pivot: the
+    //      multiplier l_ik overwrites a_ik one step LATER (nobody reads column k after step k), and the
+    //      lane that produces the next pivot also stores its reciprocal (slot 13), so that the chain per
+    //      pivot is LDS -> MUL -> FMA -> RCP -> STS.  a*(1/b) instead of a/b: <= 1 ulp, inside the stated
+    //      tolerance.  The reference's skip-exact-zero tests only skip arithmetic that changes nothing.
     {
-        const int r = lane / 5, cg = lane - 5 * r;
-        const bool act = lane < 30;
+        const int r = lane / 3, cg = lane - 3 * r;
+        const bool act = lane < 18;
+        const int s0 = 2 * cg, s1 = 2 * cg + 1;
+        if (lane == 0) As[13] = 1.0 / As[6];
+        __syncwarp();
+        double l_pend = 0.0;
+        int l_addr = -1;
         for (int k = 0; k <= N - 2; k++) {
             const int i = k + 1 + r;
             const bool on = act && i < N;
             double l = 0.0, v0 = 0.0, v1 = 0.0;
             if (on) {
-                l = As[(size_t)i * BW + (5 - r)] / As[(size_t)k * BW + 6];
-                // slot s: s<6 -> matrix column k+1+s ; s>=6 -> RHS s-6
-                const int s0 = cg, s1 = cg + 5;
-                const int src0 = (s0 < 6) ? (7 + s0) : (13 + s0 - 6);
-                const int dst0 = (s0 < 6) ? (6 + s0 - r) : (13 + s0 - 6);
-                v0 = As[(size_t)i * BW + dst0] - l * As[(size_t)k * BW + src0];
-                if (s1 < 9) {
-                    const int src1 = (s1 < 6) ? (7 + s1) : (13 + s1 - 6);
-                    const int dst1 = (s1 < 6) ? (6 + s1 - r) : (13 + s1 - 6);
-                    v1 = As[(size_t)i * BW + dst1] - l * As[(size_t)k * BW + src1];
-                }
+                const double* rk = As + (size_t)k * BW;
+                double* ri = As + (size_t)i * BW;
+                l = ri[5 - r] * rk[13];
+                v0 = ri[6 + s0 - r] - l * rk[7 + s0];
+                v1 = ri[6 + s1 - r] - l * rk[7 + s1];
+                ri[6 + s0 - r] = v0;
+                ri[6 + s1 - r] = v1;
+                if (lane == 0) ri[13] = 1.0 / v0;  // r == 0, s0 == 0: the new diagonal a_{k+1,k+1}
             }
-            __syncwarp();
-            if (on) {
-                const int s0 = cg, s1 = cg + 5;
-                const int dst0 = (s0 < 6) ? (6 + s0 - r) : (13 + s0 - 6);
-                As[(size_t)i * BW + dst0] = v0;
-                if (s1 < 9) {
-                    const int dst1 = (s1 < 6) ? (6 + s1 - r) : (13 + s1 - 6);
-                    As[(size_t)i * BW + dst1] = v1;
-                }
-                if (cg == 0) As[(size_t)i * BW + (5 - r)] = l;
-            }
+            if (l_addr >= 0) As[l_addr] = l_pend;
+            l_addr = (on && cg == 0) ? (i * BW + (5 - r)) : -1;
+            l_pend = l;
             __syncwarp();
         }
+        if (l_addr >= 0) As[l_addr] = l_pend;
+        __syncwarp();
     }
-    // ---- back substitution (trajectory.hpp:706-717): 6 rows above x 3 RHS = 18 lanes ----
-    {
-        const int r = lane / 3, d = lane - 3 * r;
-        const bool act = lane < 18;
-        for (int j = N - 1; j >= 0; j--) {
-            if (act) {
-                const double xj = As[(size_t)j * BW + 13 + d] / As[(size_t)j * BW + 6];
-                const int i = j - 1 - r;
-                if (i >= 0) As[(size_t)i * BW + 13 + d] -= As[(size_t)i * BW + (7 + r)] * xj;
-                if (r == 0) cs[3 * j + d] = xj;
+    // ---- forward substitution L y = b (trajectory.hpp:695-705) and back substitution U x = y
+    //      (:706-717), row-oriented with the last six results in a register window: lane d < 3 owns
+    //      right-hand side d; per row the dependent chain is one FMA (+ one MUL by the stored reciprocal
+    //      of the diagonal), everything else streams from shared memory.  The update order per element is
+    //      the reference's (ascending j forward, descending j backward).
+    if (lane < 3) {
+        const int d = lane;
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int base = 0; base < N; base += 6) {
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int i = base + u;
+                const double* Li = As + (size_t)i * BW;
+                double acc = cs[3 * i + d];
+#pragma unroll
+                for (int s = 0; s < 6; s++) acc -= Li[s] * w[(u + s) % 6];
+                w[u] = acc;
+                cs[3 * i + d] = acc;
             }
-            __syncwarp();
+        }
+#pragma unroll
+        for (int u = 0; u < 6; u++) w[u] = 0.0;
+        for (int base = N - 6; base >= 0; base -= 6) {
+#pragma unroll
+            for (int u = 5; u >= 0; u--) {
+                const int i = base + u;
+                const double* Ui = As + (size_t)i * BW;
+                double acc = cs[3 * i + d];
+#pragma unroll
+                for (int t = 6; t >= 1; t--) acc -= Ui[6 + t] * w[(u + t) % 6];
+                const double xi = acc * Ui[13];
+                w[u] = xi;
+                cs[3 * i + d] = xi;
+            }
         }
     }
+    __syncwarp();
     // ---- write c (6M x 3 row-major == per-piece 6x3 blocks) and the LU factors ----
     double* cg_ = bv.c + 18 * (size_t)p0;
     for (int i = lane; i < 3 * N; i += 32) cg_[i] = cs[i];
@@ -510,7 +533,7 @@ __global__ void __launch_bounds__(256) penalty_kernel(BatchView bv, PenaltyLaunc
 }
 
 // K3 ---------------------------------------------------------------------------------------------
-// smem: As[N][16] (LU factors; slots 13..15 = adjoint RHS) | gT[M] | gq[3*M] | Tc-grad[coarseN]
+// smem: As[N][16] (LU factors, slot 13 = 1/diag) | Bs[N][3] (adjoint RHS -> lambda) | gT[M] | gq[3*M] | Tc-grad[coarseN]
 __global__ void __launch_bounds__(32)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
@@ -528,7 +551,8 @@ __global__ void __launch_bounds__(32)
     double* grad = grad_out + bv.x_off[b];
     const int dimT = bv.dimT[b];
     double* As = sm;
-    double* gT = As + (size_t)N * BW;
+    double* Bs = As + (size_t)N * BW;
+    double* gT = Bs + (size_t)3 * N;
     double* gq = gT + M;
     double* gTc = gq + 3 * (size_t)M;
 
@@ -536,33 +560,44 @@ __global__ void __launch_bounds__(32)
     for (int i = lane; i < N * BW; i += 32) As[i] = lug[i];
     __syncwarp();
     const double* gdC = bv.gdC + 18 * (size_t)p0;
-    for (int i = lane; i < 3 * N; i += 32) As[(size_t)(i / 3) * BW + 13 + (i % 3)] = gdC[i];
+    for (int i = lane; i < 3 * N; i += 32) Bs[i] = gdC[i];
     __syncwarp();
 
-    // ---- A^T lambda = gdC (trajectory.hpp:724-751) ----
-    {
-        const int r = lane / 3, d = lane - 3 * r;
-        const bool act = lane < 18;
-        for (int j = 0; j <= N - 1; j++) {
-            double bj = 0.0;
-            if (act) bj = As[(size_t)j * BW + 13 + d] / As[(size_t)j * BW + 6];
-            __syncwarp();
-            if (act) {
-                const int i = j + 1 + r;
-                if (i < N) As[(size_t)i * BW + 13 + d] -= As[(size_t)j * BW + (7 + r)] * bj;  // A(j,i), i>j : U part of row j
-                if (r == 0) As[(size_t)j * BW + 13 + d] = bj;
+    // ---- A^T lambda = gdC (trajectory.hpp:724-751): U^T z = b forward, then L^T lambda = z backward,
+    //      row-oriented with a six-entry register window per right-hand side (lane d < 3), in the
+    //      reference's update order (ascending j in the first sweep, descending j in the second).
+    if (lane < 3) {
+        const int d = lane;
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int base = 0; base < N; base += 6) {
+#pragma unroll
+            for (int u = 0; u < 6; u++) {
+                const int i = base + u;
+                double acc = Bs[3 * i + d];
+#pragma unroll
+                for (int s = 6; s >= 1; s--)
+                    if (i >= s) acc -= As[(size_t)(i - s) * BW + 6 + s] * w[(u - s + 6) % 6];  // u_{i-s,i}
+                const double z = acc * As[(size_t)i * BW + 13];
+                w[u] = z;
+                Bs[3 * i + d] = z;
             }
-            __syncwarp();
         }
-        for (int j = N - 1; j >= 0; j--) {
-            if (act) {
-                const double bj = As[(size_t)j * BW + 13 + d];
-                const int i = j - 1 - r;
-                if (i >= 0) As[(size_t)i * BW + 13 + d] -= As[(size_t)j * BW + (5 - r)] * bj;  // A(j,i), i<j : L part of row j
+#pragma unroll
+        for (int u = 0; u < 6; u++) w[u] = 0.0;
+        for (int base = N - 6; base >= 0; base -= 6) {
+#pragma unroll
+            for (int u = 5; u >= 0; u--) {
+                const int i = base + u;
+                double acc = Bs[3 * i + d];
+#pragma unroll
+                for (int t = 6; t >= 1; t--)
+                    if (i + t < N) acc -= As[(size_t)(i + t) * BW + (6 - t)] * w[(u + t) % 6];  // l_{i+t,i}
+                w[u] = acc;
+                Bs[3 * i + d] = acc;
             }
-            __syncwarp();
         }
     }
+    __syncwarp();
     // ---- addPropCtoT (CPU.hpp:104-151), addPropCtoP (:154-161), rho (:989) ----
     const double* cg_ = bv.c + 18 * (size_t)p0;
     for (int i = lane; i < M; i += 32) {
@@ -580,15 +615,15 @@ __global__ void __launch_bounds__(32)
                 const double nSnp = -(24.0 * c4 + 120.0 * T1 * c5);
                 const double nCrk = -120.0 * c5;
                 const double B1[6] = {nSnp, nCrk, nVel, nVel, nAcc, nJer};
-                for (int r = 0; r < 6; r++) s += B1[r] * As[(size_t)(base + r) * BW + 13 + d];
+                for (int r = 0; r < 6; r++) s += B1[r] * Bs[3 * (base + r) + d];
             } else {
                 const double B2[3] = {nVel, nAcc, nJer};
-                for (int r = 0; r < 3; r++) s += B2[r] * As[(size_t)(base + r) * BW + 13 + d];
+                for (int r = 0; r < 3; r++) s += B2[r] * Bs[3 * (base + r) + d];
             }
         }
         gT[i] = bv.gdT[p0 + i] + s + par.rho;
         if (i < M - 1)
-            for (int d = 0; d < 3; d++) gq[3 * i + d] = As[(size_t)(6 * i + 5) * BW + 13 + d];
+            for (int d = 0; d < 3; d++) gq[3 * i + d] = Bs[3 * (6 * i + 5) + d];
     }
     __syncwarp();
     // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope ----
@@ -697,7 +732,7 @@ __global__ void __launch_bounds__(32)
 // Host-side launchers
 // ------------------------------------------------------------------------------------------------
 size_t forward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)18 * M + coarseN + 1); }
-size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)4 * M + coarseN + 1); }
+size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)18 * M + (size_t)4 * M + coarseN + 1); }
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
     PenaltyLaunch pl;

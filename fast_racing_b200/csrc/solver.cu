@@ -2,6 +2,7 @@
 #include "solver.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace frx {
@@ -52,6 +53,148 @@ __device__ __forceinline__ void block_dot2(const double* __restrict__ a, const d
         t1 += red[8 + w];
     }
     r0 = t0, r1 = t1;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Search direction d = -H g of the two-loop recursion (lbfgs.hpp:1359-1411), evaluated in the
+// coefficient space of the basis {s_l, y_l, g} ("vector-free" L-BFGS): the sequential recursion
+// (2*bound dependent dot products of length n, each a CTA-wide reduction) becomes
+//   pass 1  one streaming pass over the history: the Gram entries that involve the NEW pair and the
+//           new gradient (5 independent dot products per history slot, one warp per slot),
+//   loops   the two recursions on bound x bound Gram matrices, done by one warp in registers,
+//   pass 2  one streaming pass: d = dg*g + sum_l a_l s_l + b_l y_l.
+// Same mathematics as the reference's recursion; the summation order differs (stated tolerance).
+// Gram matrices per trajectory: SY[i][j] = s_i.y_j, SYT = SY^T, YY[i][j] = y_i.y_j (m x m each).
+// Requires m <= 128 and UPD_THREADS == 256.
+// ---------------------------------------------------------------------------------------------
+__device__ void direction_vector_free(const SolverView& sv, int b, int n, int m, int end, int bound,
+                                      const double* __restrict__ g, double* __restrict__ d, const double* __restrict__ S,
+                                      const double* __restrict__ Y, double* ysv) {
+    __shared__ double sg[128], yg[128], cb[128], ca[128], tv[128], al[128];
+    __shared__ double sh_gamma;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* SY = sv.SY + (size_t)b * m * m;
+    double* SYT = sv.SYT + (size_t)b * m * m;
+    double* YY = sv.YY + (size_t)b * m * m;
+    const double* sn = S + (size_t)end * n;
+    const double* yn = Y + (size_t)end * n;
+    // ---- pass 1 ----
+    for (int l = warp; l < bound; l += UPD_THREADS / 32) {
+        const double* sl = S + (size_t)l * n;
+        const double* yl = Y + (size_t)l * n;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+        for (int i = lane; i < n; i += 32) {
+            const double s = sl[i], y = yl[i], yni = yn[i], sni = sn[i], gi = g[i];
+            a0 += s * yni;
+            a1 += y * yni;
+            a2 += y * sni;
+            a3 += s * gi;
+            a4 += y * gi;
+        }
+        a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), a3 = warp_sum(a3), a4 = warp_sum(a4);
+        if (lane == 0) {
+            SY[(size_t)l * m + end] = a0;
+            SYT[(size_t)end * m + l] = a0;
+            YY[(size_t)l * m + end] = a1;
+            YY[(size_t)end * m + l] = a1;
+            if (l != end) {
+                SY[(size_t)end * m + l] = a2;
+                SYT[(size_t)l * m + end] = a2;
+            }
+            sg[l] = a3;
+            yg[l] = a4;
+        }
+    }
+    __syncthreads();
+    // ---- loop 1 (newest -> oldest): alpha_j = (s_j . q) / ys_j,  q -= alpha_j y_j ----
+    if (warp == 0) {
+        double bq[4] = {0, 0, 0, 0};
+        int j = end;
+        double row[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) row[q] = (lane + 32 * q < m) ? SY[(size_t)j * m + lane + 32 * q] : 0.0;
+        for (int it = 0; it < bound; it++) {
+            const int jn = (j + m - 1) % m;
+            double nxt[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) nxt[q] = (lane + 32 * q < m) ? SY[(size_t)jn * m + lane + 32 * q] : 0.0;
+            double v = bq[0] * row[0] + bq[1] * row[1] + bq[2] * row[2] + bq[3] * row[3];
+            v = warp_sum(v);
+            const double alpha = (v - sg[j]) / ysv[j];
+            if (lane == 0) al[j] = alpha;
+            if ((j & 31) == lane) bq[j >> 5] = -alpha;
+#pragma unroll
+            for (int q = 0; q < 4; q++) row[q] = nxt[q];
+            j = jn;
+        }
+        const double gamma = ysv[end] / YY[(size_t)end * m + end];  // ys / yy of the newest pair
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (lane + 32 * q < 128) cb[lane + 32 * q] = bq[q] * gamma;
+        if (lane == 0) sh_gamma = gamma;
+    }
+    __syncthreads();
+    const double dg = -sh_gamma;  // coefficient of g
+    // t_j = dg * (y_j . g) + sum_l b_l (y_j . y_l): independent of the second recursion
+    if (tid < bound) {
+        double t = 0.0;
+        for (int l = 0; l < bound; l++) t += cb[l] * YY[(size_t)l * m + tid];
+        tv[tid] = dg * yg[tid] + t;
+    }
+    __syncthreads();
+    // ---- loop 2 (oldest -> newest): beta = (y_j . r) / ys_j,  r += (alpha_j - beta) s_j ----
+    if (warp == 0) {
+        double aq[4] = {0, 0, 0, 0};
+        int j = (end + m - (bound - 1)) % m;
+        double row[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) row[q] = (lane + 32 * q < m) ? SYT[(size_t)j * m + lane + 32 * q] : 0.0;
+        for (int it = 0; it < bound; it++) {
+            const int jn = (j + 1) % m;
+            double nxt[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) nxt[q] = (lane + 32 * q < m) ? SYT[(size_t)jn * m + lane + 32 * q] : 0.0;
+            double v = aq[0] * row[0] + aq[1] * row[1] + aq[2] * row[2] + aq[3] * row[3];
+            v = warp_sum(v);
+            const double beta = (tv[j] + v) / ysv[j];
+            if ((j & 31) == lane) aq[j >> 5] = al[j] - beta;
+#pragma unroll
+            for (int q = 0; q < 4; q++) row[q] = nxt[q];
+            j = jn;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (lane + 32 * q < 128) ca[lane + 32 * q] = aq[q];
+    }
+    __syncthreads();
+    // ---- pass 2: d = dg*g + sum_l ca_l s_l + cb_l y_l ----
+    for (int base = 0; base < n; base += UPD_THREADS * 4) {
+        double acc[4];
+        int idx[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            idx[e] = base + e * UPD_THREADS + tid;
+            acc[e] = idx[e] < n ? dg * g[idx[e]] : 0.0;
+        }
+        for (int l = 0; l < bound; l++) {
+            const double a = ca[l], bb = cb[l];
+            const double* sl = S + (size_t)l * n;
+            const double* yl = Y + (size_t)l * n;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (idx[e] < n) acc[e] += a * sl[idx[e]] + bb * yl[idx[e]];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (idx[e] < n) d[idx[e]] = acc[e];
+    }
+    __syncthreads();
 }
 
 // Outcome codes shared through smem
@@ -191,6 +334,11 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
                     st->end = end1;
                 }
                 __syncthreads();
+                if (sv.vector_free) {
+                    direction_vector_free(sv, b, n, m, end, bound, g, d, S, Y, ysv);
+                    if (tid == 0) st->step = 1.0;
+                    start_iter = true;
+                } else {
                 int j = end1;
                 for (int it = 0; it < bound; it++) {
                     j = (j + m - 1) % m;
@@ -216,6 +364,7 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
                 }
                 if (tid == 0) st->step = 1.0;
                 start_iter = true;
+                }
             }
         }
     }
@@ -332,6 +481,10 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
     sv.cfg.past = 3;
     sv.cfg.g_epsilon = 1.0e-16;
     sv.cfg.min_step = 1.0e-32;
+    {
+        const char* e = getenv("FRX_LBFGS_TWO_LOOP");  // A/B switch: sequential two-loop in the reference's order
+        sv.vector_free = (e && e[0] == '1') ? 0 : 1;
+    }
     const size_t nx = (size_t)bv.total_x;
     const size_t m = (size_t)sv.cfg.mem_size;
     int* xo = nullptr;
@@ -344,6 +497,8 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
          dalloc(s, nx, &sv.xp) == cudaSuccess && dalloc(s, nx, &sv.gp) == cudaSuccess && dalloc(s, nx, &sv.d) == cudaSuccess &&
          dalloc(s, m * nx, &sv.S) == cudaSuccess && dalloc(s, m * nx, &sv.Y) == cudaSuccess &&
          dalloc(s, m * bv.B, &sv.ys) == cudaSuccess && dalloc(s, m * bv.B, &sv.alpha) == cudaSuccess &&
+         dalloc(s, m * m * bv.B, &sv.SY) == cudaSuccess && dalloc(s, m * m * bv.B, &sv.SYT) == cudaSuccess &&
+         dalloc(s, m * m * bv.B, &sv.YY) == cudaSuccess &&
          dalloc(s, (size_t)bv.B, &s->fx_dev) == cudaSuccess && dalloc(s, 1, &s->am_idx) == cudaSuccess &&
          dalloc(s, 1, &s->am_val) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->pin_int, sizeof(int) * 4) == cudaSuccess &&

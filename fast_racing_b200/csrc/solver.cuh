@@ -40,6 +40,8 @@ struct SolverView {
     double *xp, *gp, *d;           // previous iterate, its gradient, search direction
     double *S, *Y;                 // history: trajectory b, slot j at mem_size*x_off[b] + j*n_b
     double *ys, *alpha;            // mem_size per trajectory
+    double *SY, *SYT, *YY;         // mem_size^2 per trajectory: Gram matrices of the vector-free direction update
+    int vector_free;               // 1: vector-free direction update (default); 0: sequential two-loop in the reference's order
 };
 
 struct SolverState;
