@@ -250,258 +250,237 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
 }
 
 // K2 ---------------------------------------------------------------------------------------------
-// normalizeFDF (CPU.hpp:163-185): x/|x| and the symmetric Jacobian (|x|^2 I - x x^T)/|x|^3.
-struct Sym3 {
-    double xx, yy, zz, xy, xz, yz;
-};
-__device__ __forceinline__ Sym3 unit_jacobian(double a, double b, double c, double sq, double nrm) {
-    const double den = sq * nrm;
-    Sym3 G;
-    G.xx = (b * b + c * c) / den;
-    G.yy = (a * a + c * c) / den;
-    G.zz = (a * a + b * b) / den;
-    G.xy = -(a * b) / den;
-    G.xz = -(c * a) / den;
-    G.yz = -(b * c) / den;
-    return G;
-}
+// Per-sample work of MINCO_S3::addTimeIntPenalty (CPU.hpp:188-408), restructured around ADJOINT
+// 3-vectors: every penalty's dJ/dc is  beta0 (x) g0 + beta1 (x) g1 + beta2 (x) g2 + beta3 (x) g3  with
+// g_d = adjoint of (pos, vel, acc, jer) at the sample, and the time gradient is
+// alpha (g0.vel + g1.acc + g2.jer + g3.sna) + the direct v^3/K terms.  The Jacobians of the body
+// frame w.r.t. the acceleration (dxB, dyB, dzB of CPU.hpp:268-278) are never materialised: with
+//   dzB = (I - z z^T)/f,  dyB = (I - y y^T) C (I - z z^T)/(cn f),  C z = (0, z_z, -z_y),  x = y x z
+// their transposes are applied matrix-free:  dxB^T a = dyB^T (z x a) + dzB^T (a x y),
+//   dzB^T v = (v - z (z.v))/f ,   dyB^T v = (I - z z^T) C^T (I - y y^T) v / (cn f).
+// Same mathematics as the reference, different association (inside the stated tolerance).
+//
+// smem: cf[ppc][60] derivative coefficient tables | fc[ppc][6*max_faces] | part[20][threads]
+#define PEN_THREADS 256
+#define CF 60  // per piece: 18 pos + 15 vel + 12 acc + 9 jerk + 6 snap coefficients
 
-// smem: cblk[ppc][18] | fc[ppc][6*max_faces] | part[ppc*tpp][20]
-__global__ void __launch_bounds__(256) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
+__global__ void __launch_bounds__(PEN_THREADS, 2) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int gp_base = blockIdx.x * pl.ppc;
     const int npieces = min(pl.ppc, bv.total_pieces - gp_base);
-    double* cblk = sm;
-    double* fc = cblk + (size_t)pl.ppc * 18;
+    double* cf = sm;
+    double* fc = cf + (size_t)pl.ppc * CF;
     double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
 
-    // ---- stage the 6x3 coefficient blocks and the face lists of this CTA's pieces ----
-    for (int i = tid; i < npieces * 18; i += blockDim.x) cblk[i] = bv.c[18 * (size_t)gp_base + i];
+    // ---- stage: polynomial coefficient tables (c and its first four derivatives, per axis) and face lists ----
+    for (int i = tid; i < npieces * 18; i += PEN_THREADS) {
+        const int p = i / 18, e = i - 18 * p, k = e / 3, d = e - 3 * k;
+        const double v = bv.c[18 * (size_t)gp_base + i];
+        double* t = cf + (size_t)p * CF;
+        t[3 * k + d] = v;                                                                     // pos:  c_k
+        if (k >= 1) t[18 + 3 * (k - 1) + d] = v * (double)k;                                  // vel:  k c_k
+        if (k >= 2) t[33 + 3 * (k - 2) + d] = v * (double)(k * (k - 1));                      // acc
+        if (k >= 3) t[45 + 3 * (k - 3) + d] = v * (double)(k * (k - 1) * (k - 2));            // jerk
+        if (k >= 4) t[54 + 3 * (k - 4) + d] = v * (double)(k * (k - 1) * (k - 2) * (k - 3));  // snap
+    }
     for (int p = 0; p < npieces; p++) {
         const int gp = gp_base + p;
         const int nf = bv.piece_face_cnt[gp] * 6;
         const double* src = bv.faces + 6 * (size_t)bv.piece_face_off[gp];
         double* dst = fc + (size_t)p * 6 * bv.max_faces;
-        for (int i = tid; i < nf; i += blockDim.x) dst[i] = src[i];
+        for (int i = tid; i < nf; i += PEN_THREADS) dst[i] = src[i];
     }
+#pragma unroll
+    for (int v = 0; v < 20; v++) part[v * PEN_THREADS + tid] = 0.0;
     __syncthreads();
 
     const int pl_piece = tid / pl.tpp;
     const int chunk = tid - pl_piece * pl.tpp;
-    double acc[20];
-#pragma unroll
-    for (int i = 0; i < 20; i++) acc[i] = 0.0;
+    double* acc = part + tid;  // acc[v * PEN_THREADS]
 
     if (pl_piece < npieces && !(bv.active && !bv.active[bv.piece_traj[gp_base + pl_piece]])) {
         const int gp = gp_base + pl_piece;
-        const DevParams& P = bv.par[bv.piece_traj[gp]];
-        const double* c = cblk + pl_piece * 18;
+        const DevParams* __restrict__ P = bv.par + bv.piece_traj[gp];
+        const double* t = cf + (size_t)pl_piece * CF;
         const double* faces = fc + (size_t)pl_piece * 6 * bv.max_faces;
         const int F = bv.piece_face_cnt[gp];
         const int K = bv.cons[gp];
         const int S = K + 1;
-        const double Ti = bv.T[gp];
-        const double step = Ti / K;
+        const double step = bv.T[gp] / K;
         const double invK = 1.0 / K;
         const int j0 = chunk * pl.spt;
         const int j1 = min(j0 + pl.spt, S);
         // running-sum abscissa exactly as the reference: s1 = 0; s1 += step (CPU.hpp:246,400)
         double s1 = 0.0;
         for (int j = 0; j < j0 && j < S; j++) s1 += step;
-        const double ex = P.ell[0], ey = P.ell[1], ez = P.ell[2];
+        const double ex = P->ell[0], ey = P->ell[1], ez = P->ell[2];
+        const double emax = fmax(ex, fmax(ey, ez));
+        const double chi0 = P->chi[0], chi1 = P->chi[1], chi2 = P->chi[2], chi3 = P->chi[3];
+        const double margin = P->margin, gacc = P->gacc;
+        const double vmax_sqr = P->vmax_sqr, thrmin_sqr = P->thrmin_sqr, thrmax_sqr = P->thrmax_sqr, bdrmax_sqr = P->bdrmax_sqr;
 
         for (int j = j0; j < j1; j++) {
-            const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
             const double alpha = invK * j;
             const double omg = (j == 0 || j == S - 1) ? 0.5 : 1.0;
             const double w = omg * step;
             double pos[3], vel[3], ac[3], jer[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
-                const double c0 = c[d], c1 = c[3 + d], c2 = c[6 + d], c3 = c[9 + d], c4 = c[12 + d], c5 = c[15 + d];
-                pos[d] = c0 + c1 * s1 + c2 * s2 + c3 * s3 + c4 * s4 + c5 * s5;
-                vel[d] = c1 + c2 * (2.0 * s1) + c3 * (3.0 * s2) + c4 * (4.0 * s3) + c5 * (5.0 * s4);
-                ac[d] = c2 * 2.0 + c3 * (6.0 * s1) + c4 * (12.0 * s2) + c5 * (20.0 * s3);
-                jer[d] = c3 * 6.0 + c4 * (24.0 * s1) + c5 * (60.0 * s2);
+                pos[d] = ((((t[15 + d] * s1 + t[12 + d]) * s1 + t[9 + d]) * s1 + t[6 + d]) * s1 + t[3 + d]) * s1 + t[d];
+                vel[d] = (((t[30 + d] * s1 + t[27 + d]) * s1 + t[24 + d]) * s1 + t[21 + d]) * s1 + t[18 + d];
+                ac[d] = ((t[42 + d] * s1 + t[39 + d]) * s1 + t[36 + d]) * s1 + t[33 + d];
+                jer[d] = (t[51 + d] * s1 + t[48 + d]) * s1 + t[45 + d];
             }
             // body frame (CPU.hpp:266-279)
-            const double hx = ac[0], hy = ac[1], hz = ac[2] + P.gacc;
+            const double hx = ac[0], hy = ac[1], hz = ac[2] + gacc;
             const double hsq = hx * hx + hy * hy + hz * hz;
             const double fThr = sqrt(hsq);
-            const double zx = hx / fThr, zy = hy / fThr, zz = hz / fThr;
-            // czB = (0, zz, -zy)
-            const double csq = zz * zz + zy * zy;
-            const double cn = sqrt(csq);
-            const double yx = 0.0, yy = zz / cn, yz = -zy / cn;
-            // xB = yB x zB
-            const double xx = yy * zz - yz * zy, xy = yz * zx - yx * zz, xz = yx * zy - yy * zx;
+            const double inv_f = 1.0 / fThr;
+            const double zx = hx * inv_f, zy = hy * inv_f, zz = hz * inv_f;
+            const double cn = sqrt(zz * zz + zy * zy);
+            const double inv_cn = 1.0 / cn;
+            const double yy = zz * inv_cn, yz = -zy * inv_cn;                 // yB = (0, yy, yz)
+            const double xx = yy * zz - yz * zy, xy = yz * zx, xz = -yy * zx;  // xB = yB x zB
 
-            // adjoint 3-vectors of pos / vel / acc / jer for this sample, plus the pieces that do
-            // not go through them
             double g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, g3[3] = {0, 0, 0};
-            double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef*e_m*n  (m = x,y,z body axis)
+            double uy[3] = {0, 0, 0}, uz[3] = {0, 0, 0};  // arguments of dyB^T and dzB^T
             double cst = 0.0, direct = 0.0;
-            bool sfc_on = false;
+            bool any = false, jac = false;
 
-            // ---- safe-flight-corridor faces (CPU.hpp:310-345) ----
-            if (P.chi[0] != 0.0) {  // chi0 == 0 adds exact zeros in the reference
-                for (int k = 0; k < F; k++) {
-                    const double nx = faces[6 * k], ny = faces[6 * k + 1], nz = faces[6 * k + 2];
-                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
-                    const double uy = (yx * nx + yy * ny + yz * nz) * ey;
-                    const double uz = (zx * nx + zy * ny + zz * nz) * ez;
-                    const double eNorm = sqrt(ux * ux + uy * uy + uz * uz);
-                    const double sd = nx * (pos[0] - faces[6 * k + 3]) + ny * (pos[1] - faces[6 * k + 4]) +
-                                      nz * (pos[2] - faces[6 * k + 5]) + eNorm + P.margin;
-                    if (sd > 0.0) {
-                        const double sd2 = sd * sd, sd3 = sd * sd2;
-                        const double coef = w * P.chi[0] * 3.0 * sd2;
-                        const double e0 = ux / eNorm * ex, e1 = uy / eNorm * ey, e2 = uz / eNorm * ez;
-                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
-                        ax[0] += coef * e0 * nx, ax[1] += coef * e0 * ny, ax[2] += coef * e0 * nz;
-                        ay[0] += coef * e1 * nx, ay[1] += coef * e1 * ny, ay[2] += coef * e1 * nz;
-                        az[0] += coef * e2 * nx, az[1] += coef * e2 * ny, az[2] += coef * e2 * nz;
-                        cst += w * P.chi[0] * sd3;
-                        direct += omg * P.chi[0] * sd3 * invK;
-                        sfc_on = true;
-                    }
-                }
-            }
             // ---- velocity (CPU.hpp:347-359) ----
-            const double violaVel = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - P.vmax_sqr;
+            const double violaVel = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - vmax_sqr;
             if (violaVel > 0.0) {
                 const double v2 = violaVel * violaVel, v3 = v2 * violaVel;
-                const double coef = w * P.chi[1] * (3.0 * v2) * 2.0;
-                g1[0] += coef * vel[0], g1[1] += coef * vel[1], g1[2] += coef * vel[2];
-                cst += w * P.chi[1] * v3;
-                direct += omg * P.chi[1] * v3 * invK;
+                const double coef = w * chi1 * (3.0 * v2) * 2.0;
+                g1[0] = coef * vel[0], g1[1] = coef * vel[1], g1[2] = coef * vel[2];
+                cst += w * chi1 * v3;
+                direct += omg * chi1 * v3 * invK;
+                any = true;
             }
             // ---- thrust (CPU.hpp:361-385) ----
             const double sqrMagThr = fThr * fThr;
-            const double violaThrl = P.thrmin_sqr - sqrMagThr;
-            const double violaThrh = sqrMagThr - P.thrmax_sqr;
-            if (violaThrl > 0.0) {
-                const double v2 = violaThrl * violaThrl, v3 = v2 * violaThrl;
-                const double coef = -(w * P.chi[2] * (3.0 * v2) * 2.0);
-                g2[0] += coef * hx, g2[1] += coef * hy, g2[2] += coef * hz;
-                cst += w * P.chi[2] * v3;
-                direct += omg * P.chi[2] * v3 * invK;
-            }
-            if (violaThrh > 0.0) {
-                const double v2 = violaThrh * violaThrh, v3 = v2 * violaThrh;
-                const double coef = w * P.chi[2] * (3.0 * v2) * 2.0;
-                g2[0] += coef * hx, g2[1] += coef * hy, g2[2] += coef * hz;
-                cst += w * P.chi[2] * v3;
-                direct += omg * P.chi[2] * v3 * invK;
+            const double violaThrl = thrmin_sqr - sqrMagThr;
+            const double violaThrh = sqrMagThr - thrmax_sqr;
+            if (violaThrl > 0.0 || violaThrh > 0.0) {
+                const double v = violaThrl > 0.0 ? violaThrl : violaThrh;
+                const double v2 = v * v, v3 = v2 * v;
+                const double coef = (violaThrl > 0.0 ? -1.0 : 1.0) * (w * chi2 * (3.0 * v2) * 2.0);
+                g2[0] = coef * hx, g2[1] = coef * hy, g2[2] = coef * hz;
+                cst += w * chi2 * v3;
+                direct += omg * chi2 * v3 * invK;
+                any = true;
             }
             // ---- body rate (CPU.hpp:285-304, 387-398) ----
-            const double r0 = xx * jer[0] + xy * jer[1] + xz * jer[2];
-            const double r1 = yx * jer[0] + yy * jer[1] + yz * jer[2];
-            const double r2 = zx * jer[0] + zy * jer[1] + zz * jer[2];
-            const double bd0 = r0 / fThr, bd1 = r1 / fThr;
-            const double violaBdr = bd1 * bd1 + bd0 * bd0 - P.bdrmax_sqr;
-            const bool bdr_on = violaBdr > 0.0;
-
-            if (sfc_on || bdr_on) {
-                // Jacobians of the frame w.r.t. acc (CPU.hpp:268-278): dzB symmetric; dyB = dn * cdzB;
-                // dxB[:,m] = dyB[:,m] x zB + yB x dzB[:,m]
-                const Sym3 Z = unit_jacobian(hx, hy, hz, hsq, fThr);
-                const Sym3 Cn = unit_jacobian(0.0, zz, -zy, csq, cn);
-                // cdzB rows: 0 ; dzB.row(2) ; -dzB.row(1)
-                const double cd1[3] = {Z.xz, Z.yz, Z.zz};
-                const double cd2[3] = {-Z.xy, -Z.yy, -Z.yz};
-                double dY[3][3], dX[3][3];
-                const double dZ[3][3] = {{Z.xx, Z.xy, Z.xz}, {Z.xy, Z.yy, Z.yz}, {Z.xz, Z.yz, Z.zz}};
-#pragma unroll
-                for (int m = 0; m < 3; m++) {
-                    dY[0][m] = Cn.xy * cd1[m] + Cn.xz * cd2[m];
-                    dY[1][m] = Cn.yy * cd1[m] + Cn.yz * cd2[m];
-                    dY[2][m] = Cn.yz * cd1[m] + Cn.zz * cd2[m];
-                }
-#pragma unroll
-                for (int m = 0; m < 3; m++) {
-                    // dyB.col(m) x zB + yB x dzB.col(m)
-                    dX[0][m] = (dY[1][m] * zz - dY[2][m] * zy) + (yy * dZ[2][m] - yz * dZ[1][m]);
-                    dX[1][m] = (dY[2][m] * zx - dY[0][m] * zz) + (yz * dZ[0][m] - yx * dZ[2][m]);
-                    dX[2][m] = (dY[0][m] * zy - dY[1][m] * zx) + (yx * dZ[1][m] - yy * dZ[0][m]);
-                }
-                if (sfc_on) {
-                    // g2 += sum_m dB_m^T a_m  (w of SURVEY A.4 summed over active faces)
-#pragma unroll
-                    for (int cc = 0; cc < 3; cc++) {
-                        g2[cc] += (dX[0][cc] * ax[0] + dX[1][cc] * ax[1] + dX[2][cc] * ax[2]) +
-                                  (dY[0][cc] * ay[0] + dY[1][cc] * ay[1] + dY[2][cc] * ay[2]) +
-                                  (dZ[0][cc] * az[0] + dZ[1][cc] * az[1] + dZ[2][cc] * az[2]);
-                    }
-                }
-                if (bdr_on) {
+            {
+                const double r0 = xx * jer[0] + xy * jer[1] + xz * jer[2];
+                const double r1 = yy * jer[1] + yz * jer[2];
+                const double r2 = zx * jer[0] + zy * jer[1] + zz * jer[2];
+                const double bd0 = r0 * inv_f, bd1 = r1 * inv_f;
+                const double violaBdr = bd1 * bd1 + bd0 * bd0 - bdrmax_sqr;
+                if (violaBdr > 0.0) {
                     const double v2 = violaBdr * violaBdr, v3 = v2 * violaBdr;
-                    const double coef = w * P.chi[3] * (3.0 * v2);
-                    // dSqrMagBdr = 2 bd0 dBdr.row(0) + 2 bd1 dBdr.row(1),
-                    // dBdr = -r dfThr^T / f^2 - R^T (dxB r0 + dyB r1 + dzB r2) / f        (CPU.hpp:293-296)
+                    const double coef = w * chi3 * (3.0 * v2);
                     const double t0 = 2.0 * bd0, t1 = 2.0 * bd1;
-                    const double wv[3] = {t0 * xx + t1 * yx, t0 * xy + t1 * yy, t0 * xz + t1 * yz};
-                    const double hfac = (t0 * r0 + t1 * r1) / (sqrMagThr * fThr);
-                    const double hh[3] = {hx, hy, hz};
-                    const double Rx[3] = {xx, xy, xz}, Ry[3] = {yx, yy, yz};
-#pragma unroll
-                    for (int cc = 0; cc < 3; cc++) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int m = 0; m < 3; m++) s += wv[m] * (dX[m][cc] * r0 + dY[m][cc] * r1 + dZ[m][cc] * r2);
-                        const double dS = -hfac * hh[cc] - s / fThr;
-                        const double dJ = (t1 * Ry[cc] + t0 * Rx[cc]) / fThr;  // dJerSqrMagBdr (CPU.hpp:297-299)
-                        g2[cc] += coef * dS;
-                        g3[cc] += coef * dJ;
-                    }
-                    cst += w * P.chi[3] * v3;
-                    direct += omg * P.chi[3] * v3 * invK;
+                    const double wx = t0 * xx, wy = t0 * xy + t1 * yy, wz = t0 * xz + t1 * yz;  // wv = t0 xB + t1 yB
+                    // dSqrMagBdr = -hfac h - (1/f) [ dyB^T(r0 (z x wv) + r1 wv) + dzB^T(r0 (wv x y) + r2 wv) ]
+                    const double hfac = (t0 * r0 + t1 * r1) * inv_f * inv_f * inv_f;
+                    const double k0 = -coef * inv_f;
+                    const double zwx = zy * wz - zz * wy, zwy = zz * wx - zx * wz, zwz = zx * wy - zy * wx;  // z x wv
+                    const double wyx = wy * yz - wz * yy, wyy = -wx * yz, wyz = wx * yy;                      // wv x y
+                    uy[0] = k0 * (r0 * zwx + r1 * wx), uy[1] = k0 * (r0 * zwy + r1 * wy), uy[2] = k0 * (r0 * zwz + r1 * wz);
+                    uz[0] = k0 * (r0 * wyx + r2 * wx), uz[1] = k0 * (r0 * wyy + r2 * wy), uz[2] = k0 * (r0 * wyz + r2 * wz);
+                    const double kh = -coef * hfac;
+                    g2[0] += kh * hx, g2[1] += kh * hy, g2[2] += kh * hz;
+                    const double kj = coef * inv_f;  // dJerSqrMagBdr = wv / f (CPU.hpp:297-299)
+                    g3[0] = kj * wx, g3[1] = kj * wy, g3[2] = kj * wz;
+                    cst += w * chi3 * v3;
+                    direct += omg * chi3 * v3 * invK;
+                    any = true, jac = true;
                 }
             }
-            if (sfc_on || bdr_on || violaVel > 0.0 || violaThrl > 0.0 || violaThrh > 0.0) {
+            // ---- safe-flight-corridor faces (CPU.hpp:310-345) ----
+            if (chi0 != 0.0) {  // chi0 == 0 adds exact zeros in the reference
+                double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef * e_m * n
+                bool sfc_on = false;
+                for (int k = 0; k < F; k++) {
+                    const double nx = faces[6 * k], ny = faces[6 * k + 1], nz = faces[6 * k + 2];
+                    const double nd = nx * (pos[0] - faces[6 * k + 3]) + ny * (pos[1] - faces[6 * k + 4]) + nz * (pos[2] - faces[6 * k + 5]);
+                    // |E R^T n| <= emax: faces farther than emax + margin cannot be active
+                    if (nd + margin + emax < -1.0e-9) continue;
+                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
+                    const double uyv = (yy * ny + yz * nz) * ey;
+                    const double uzv = (zx * nx + zy * ny + zz * nz) * ez;
+                    const double eNorm = sqrt(ux * ux + uyv * uyv + uzv * uzv);
+                    const double sd = nd + eNorm + margin;
+                    if (sd > 0.0) {
+                        const double sd2 = sd * sd, sd3 = sd * sd2;
+                        const double coef = w * chi0 * 3.0 * sd2;
+                        const double ie = 1.0 / eNorm;
+                        const double e0 = coef * (ux * ie * ex), e1 = coef * (uyv * ie * ey), e2 = coef * (uzv * ie * ez);
+                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
+                        ax[0] += e0 * nx, ax[1] += e0 * ny, ax[2] += e0 * nz;
+                        ay[0] += e1 * nx, ay[1] += e1 * ny, ay[2] += e1 * nz;
+                        az[0] += e2 * nx, az[1] += e2 * ny, az[2] += e2 * nz;
+                        cst += w * chi0 * sd3;
+                        direct += omg * chi0 * sd3 * invK;
+                        sfc_on = true;
+                    }
+                }
+                if (sfc_on) {
+                    // dxB^T ax + dyB^T ay + dzB^T az = dyB^T (ay + z x ax) + dzB^T (az + ax x y)
+                    uy[0] += ay[0] + (zy * ax[2] - zz * ax[1]);
+                    uy[1] += ay[1] + (zz * ax[0] - zx * ax[2]);
+                    uy[2] += ay[2] + (zx * ax[1] - zy * ax[0]);
+                    uz[0] += az[0] + (ax[1] * yz - ax[2] * yy);
+                    uz[1] += az[1] + (-ax[0] * yz);
+                    uz[2] += az[2] + (ax[0] * yy);
+                    any = true, jac = true;
+                }
+            }
+            if (jac) {
+                // g2 += dzB^T uz + dyB^T uy
+                const double zu = zx * uz[0] + zy * uz[1] + zz * uz[2];
+                g2[0] += (uz[0] - zx * zu) * inv_f, g2[1] += (uz[1] - zy * zu) * inv_f, g2[2] += (uz[2] - zz * zu) * inv_f;
+                const double yu = yy * uy[1] + yz * uy[2];
+                const double t1y = uy[1] - yy * yu, t1z = uy[2] - yz * yu;  // (I - y y^T) uy; its x component is unused by C^T
+                const double cy = -t1z, cz = t1y;                            // C^T t1 = (0, -t1z, t1y)
+                const double zc = zy * cy + zz * cz;
+                const double kk = inv_cn * inv_f;
+                g2[0] += (-zx * zc) * kk, g2[1] += (cy - zy * zc) * kk, g2[2] += (cz - zz * zc) * kk;
+            }
+            if (any) {
+                const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
                 // dJ/dc += beta0 (x) g0 + beta1 (x) g1 + beta2 (x) g2 + beta3 (x) g3
-                const double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
-                const double b2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
-                const double b3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
-                const double b0[6] = {1.0, s1, s2, s3, s4, s5};
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    acc[0 + d] += b0[0] * g0[d];
-                    acc[3 + d] += b0[1] * g0[d] + b1[1] * g1[d];
-                    acc[6 + d] += b0[2] * g0[d] + b1[2] * g1[d] + b2[2] * g2[d];
-                    acc[9 + d] += b0[3] * g0[d] + b1[3] * g1[d] + b2[3] * g2[d] + b3[3] * g3[d];
-                    acc[12 + d] += b0[4] * g0[d] + b1[4] * g1[d] + b2[4] * g2[d] + b3[4] * g3[d];
-                    acc[15 + d] += b0[5] * g0[d] + b1[5] * g1[d] + b2[5] * g2[d] + b3[5] * g3[d];
+                    acc[(0 + d) * PEN_THREADS] += g0[d];
+                    acc[(3 + d) * PEN_THREADS] += s1 * g0[d] + g1[d];
+                    acc[(6 + d) * PEN_THREADS] += s2 * g0[d] + (2.0 * s1) * g1[d] + 2.0 * g2[d];
+                    acc[(9 + d) * PEN_THREADS] += s3 * g0[d] + (3.0 * s2) * g1[d] + (6.0 * s1) * g2[d] + 6.0 * g3[d];
+                    acc[(12 + d) * PEN_THREADS] += s4 * g0[d] + (4.0 * s3) * g1[d] + (12.0 * s2) * g2[d] + (24.0 * s1) * g3[d];
+                    acc[(15 + d) * PEN_THREADS] += s5 * g0[d] + (5.0 * s4) * g1[d] + (20.0 * s3) * g2[d] + (60.0 * s2) * g3[d];
                 }
-                // time gradient: alpha * (g0.vel + g1.acc + g2.jer + g3.sna) + the v^3/K terms
-                const double sn0 = c[12] * 24.0 + c[15] * (120.0 * s1);
-                const double sn1 = c[13] * 24.0 + c[16] * (120.0 * s1);
-                const double sn2 = c[14] * 24.0 + c[17] * (120.0 * s1);
-                acc[18] += alpha * ((g0[0] * vel[0] + g0[1] * vel[1] + g0[2] * vel[2]) +
-                                    (g1[0] * ac[0] + g1[1] * ac[1] + g1[2] * ac[2]) +
-                                    (g2[0] * jer[0] + g2[1] * jer[1] + g2[2] * jer[2]) +
-                                    (g3[0] * sn0 + g3[1] * sn1 + g3[2] * sn2)) +
-                           direct;
-                acc[19] += cst;
+                const double sn0 = t[57] * s1 + t[54], sn1 = t[58] * s1 + t[55], sn2 = t[59] * s1 + t[56];
+                acc[18 * PEN_THREADS] += alpha * ((g0[0] * vel[0] + g0[1] * vel[1] + g0[2] * vel[2]) +
+                                                  (g1[0] * ac[0] + g1[1] * ac[1] + g1[2] * ac[2]) +
+                                                  (g2[0] * jer[0] + g2[1] * jer[1] + g2[2] * jer[2]) +
+                                                  (g3[0] * sn0 + g3[1] * sn1 + g3[2] * sn2)) +
+                                         direct;
+                acc[19 * PEN_THREADS] += cst;
             }
             s1 += step;
         }
     }
-    // ---- fixed-order reduction of the per-thread partials into per-piece sums ----
-    {
-        double* mine = part + (size_t)tid * 20;
-#pragma unroll
-        for (int i = 0; i < 20; i++) mine[i] = acc[i];
-    }
     __syncthreads();
-    for (int task = tid; task < npieces * 20; task += blockDim.x) {
+    // ---- fixed-order reduction of the per-thread partials into per-piece sums ----
+    for (int task = tid; task < npieces * 20; task += PEN_THREADS) {
         const int p = task / 20, v = task - p * 20;
         const int gp = gp_base + p;
-        const double* src = part + (size_t)p * pl.tpp * 20 + v;
+        const double* src = part + (size_t)v * PEN_THREADS + p * pl.tpp;
         double s = 0.0;
-        for (int t = 0; t < pl.tpp; t++) s += src[(size_t)t * 20];
-        const double* c = cblk + p * 18;
+        for (int q = 0; q < pl.tpp; q++) s += src[q];
+        const double* c = cf + (size_t)p * CF;
         const double T1 = bv.T[gp], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
         if (v < 18) {
             // energy gradient w.r.t. c rows 3..5 (CPU.hpp:80-95), added first as in the reference
@@ -750,7 +729,7 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
     pl.ppc = pl.threads / pl.tpp;
     if (pl.ppc < 1) pl.ppc = 1;
     pl.grid = (bv.total_pieces + pl.ppc - 1) / pl.ppc;
-    pl.smem = sizeof(double) * ((size_t)pl.ppc * 18 + (size_t)pl.ppc * 6 * bv.max_faces + (size_t)pl.threads * 20);
+    pl.smem = sizeof(double) * ((size_t)pl.ppc * 60 + (size_t)pl.ppc * 6 * bv.max_faces + (size_t)pl.threads * 20);
     return pl;
 }
 
