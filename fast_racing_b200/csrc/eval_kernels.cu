@@ -22,8 +22,8 @@ namespace frx {
 // ------------------------------------------------------------------------------------------------
 // Band storage used on the device: row-major, 16 doubles per row: slot (j - i + 6) for column j of
 // row i (13 diagonals, bandwidth 6/6 as trajectory.hpp:645 with N-major order swapped for coalesced
-// row access), slot 13 = reciprocal of the U diagonal, slots 14..15 unused.  After the factorisation slots
-// 0..5 hold the multipliers l_{i,i-6..i-1}, 6 the diagonal of U, 7..12 its upper band.
+// row access).  After the factorisation slots 0..5 hold the multipliers l_{i,i-6..i-1}, slot 6 the RECIPROCAL of
+// the U diagonal, 7..12 the upper band of U, 13..15 the forward-substituted right-hand side.
 // ------------------------------------------------------------------------------------------------
 #define BW 16
 
@@ -32,12 +32,84 @@ __device__ __forceinline__ double c2_forward(double t) {  // CPU.hpp:639-641
 }
 
 // K1 ---------------------------------------------------------------------------------------------
-// smem: As[N][16] | cs[N][3] | Tc[coarseN]
-__global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
+// One trajectory per CTA of two warps.
+//   warp 0  runs the dependent chain: the 6M-1 pivots of the banded LU (trajectory.hpp:655-687) with the
+//           forward substitution of the three right-hand sides fused in (:695-705), on a 32-row ring of the
+//           band in shared memory; then the back substitution (:706-717).
+//   warp 1  keeps the chain fed: it fills the rows of the junction two pieces ahead from a constant entry
+//           table (MINCO_S3::generate, CPU.hpp:437-499), and retires finished rows: LU factors to global
+//           memory for the adjoint solve of K3, (1/u_ii, U row, y) into a compact shared store for the back
+//           substitution.  The warps meet at one barrier per piece (6 pivots).
+// Only ~(4 + 0.5 M) KB of shared memory per trajectory, so a 1024-trajectory batch is resident in one wave.
+//
+// Ring row layout (16 doubles): [0..5] multipliers l_{i,i-6..i-1} | [6] 1/u_ii once final (the diagonal
+// before) | [7..12] u_{i,i+1..i+6} | [13..15] right-hand side (x,y,z).  Rows are retired to bv.lu in the
+// same layout.
+#define RING 32
+__device__ long long g_clk[32];
+#define CLK(slot) do { if (blockIdx.x == 0 && lane == 0) g_clk[(slot) + 16 * warp] = clock64(); } while (0)
+#define UST 9  // compact store per row, pre-multiplied by 1/u_ii: u_{i,i+1..i+6}/u_ii, y_{x,y,z}/u_ii
+
+// Entry tables of one junction block (rows 6i+3 .. 6i+8, CPU.hpp:446-476): value = coef * T^pow at
+// (row offset, band slot = column - row + 6).
+__constant__ int JR[31] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
+__constant__ int JS[31] = {6, 7, 8, 12, 6, 7, 12, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 6, 0, 1, 2, 3, 6};
+__constant__ double JC[31] = {6.0, 24.0, 60.0, -6.0, 24.0, 120.0, -24.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
+                              1.0, 1.0, -1.0, 1.0, 2.0, 3.0, 4.0, 5.0, -1.0, 2.0, 6.0, 12.0, 20.0, -2.0};
+__constant__ int JP[31] = {0, 1, 2, 0, 0, 1, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 0};
+// Tail block (rows 6M-3 .. 6M-1, CPU.hpp:481-495), T of the last piece.
+__constant__ int TR[15] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2};
+__constant__ int TS[15] = {3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 3, 4, 5, 6};
+__constant__ double TC[15] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 4.0, 5.0, 2.0, 6.0, 12.0, 20.0};
+__constant__ int TP[15] = {0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3};
+
+__device__ __forceinline__ double pick_pow(int p, double T1, double T2, double T3, double T4, double T5) {
+    return p == 0 ? 1.0 : (p == 1 ? T1 : (p == 2 ? T2 : (p == 3 ? T3 : (p == 4 ? T4 : T5))));
+}
+
+// Fill the rows of block `g` (g = -1: head rows 0..2; 0 <= g <= M-2: junction g; g = M-1: tail rows) into
+// the ring, executed by one full warp (lane = 0..31).
+__device__ __forceinline__ void fill_block(double* ring, const BatchView& bv, int b, int p0, int M, int g, int lane) {
+    const int N = 6 * M;
+    if (g < -1 || g > M - 1) return;
+    const int row0 = (g < 0) ? 0 : ((g == M - 1) ? N - 3 : 6 * g + 3);
+    const int nrows = (g < 0 || g == M - 1) ? 3 : 6;
+    for (int e = lane; e < nrows * BW; e += 32) ring[((row0 + e / BW) & (RING - 1)) * BW + (e % BW)] = 0.0;
+    __syncwarp();
+    if (g < 0) {
+        const double* ht = bv.headtail + 18 * (size_t)b;
+        if (lane < 3) ring[(lane & (RING - 1)) * BW + 6] = (lane == 2) ? 2.0 : 1.0;  // A(0,0)=1, A(1,1)=1, A(2,2)=2
+        if (lane < 9) ring[((lane / 3) & (RING - 1)) * BW + 13 + lane % 3] = ht[lane];  // rows 0,1,2 <- head p, v, a
+    } else if (g < M - 1) {
+        const double T1 = bv.T[p0 + g], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        if (lane < 31) ring[((row0 + JR[lane]) & (RING - 1)) * BW + JS[lane]] = JC[lane] * pick_pow(JP[lane], T1, T2, T3, T4, T5);
+        if (lane < 3) ring[((row0 + 2) & (RING - 1)) * BW + 13 + lane] = bv.q[3 * (size_t)(p0 + g) + lane];  // waypoint row 6g+5
+    } else {
+        const double T1 = bv.T[p0 + M - 1], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        const double* ht = bv.headtail + 18 * (size_t)b + 9;
+        if (lane < 15) ring[((row0 + TR[lane]) & (RING - 1)) * BW + TS[lane]] = TC[lane] * pick_pow(TP[lane], T1, T2, T3, T4, T5);
+        if (lane < 9) ring[((row0 + lane / 3) & (RING - 1)) * BW + 13 + lane % 3] = ht[lane];
+    }
+    __syncwarp();
+}
+
+// Retire rows [row0, row0+cnt): factors to global (same 16-double layout), compact store for back substitution.
+__device__ __forceinline__ void retire_rows(const double* ring, double* lug, double* ust, int row0, int cnt, int lane) {
+    for (int e = lane; e < cnt * BW; e += 32) lug[(size_t)row0 * BW + e] = ring[((row0 + e / BW) & (RING - 1)) * BW + (e % BW)];
+    for (int e = lane; e < cnt * UST; e += 32) {
+        const int rr = e / UST, q = e - UST * rr;
+        const double* rw = ring + ((row0 + rr) & (RING - 1)) * BW;
+        ust[(size_t)(row0 + rr) * UST + q] = rw[7 + q] * rw[6];  // x_i = y_i/u_ii - sum_t (u_{i,i+t}/u_ii) x_{i+t}
+    }
+}
+
+// smem: ring[RING][16] | ust[N][10] | Tc[coarseN]
+__global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (bv.active && !bv.active[b]) return;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
     const int M = bv.piece_off[b + 1] - p0;
     const int N = 6 * M;
@@ -46,36 +118,32 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
     const DevParams par = bv.par[b];
     const double* x = xin + bv.x_off[b];
     const int dimT = bv.dimT[b];
-    double* As = sm;
-    double* cs = As + (size_t)N * BW;
-    double* Tc = cs + (size_t)N * 3;
+    double* ring = sm;
+    double* ust = ring + RING * BW;
+    double* Tc = ust;  // coarse durations: dead before the first row is retired into ust
+    CLK(0);
 
     // ---- forwardT (CPU.hpp:626-676) ----
     if (par.softT) {
-        for (int i = lane; i < coarseN; i += 32) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
-    } else {
-        if (lane == 0) {  // fixed total time: sequential sums as in the reference (rare path)
-            const int Ms1 = dimT;
-            for (int i = 0; i < Ms1; i++) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
-            Tc[Ms1] = 0.0;
-            double s = 0.0;
-            for (int i = 0; i <= Ms1; i++) s += Tc[i];
-            const double den = 1.0 + s;
-            for (int i = 0; i <= Ms1; i++) Tc[i] /= den;
-            s = 0.0;
-            for (int i = 0; i <= Ms1; i++) s += Tc[i];
-            Tc[Ms1] = 1.0 - s;
-            for (int i = 0; i <= Ms1; i++) Tc[i] *= par.sumT;
-        }
+        for (int i = tid; i < coarseN; i += 64) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+    } else if (tid == 0) {  // fixed total time: sequential sums as in the reference (rare path)
+        const int Ms1 = dimT;
+        for (int i = 0; i < Ms1; i++) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+        Tc[Ms1] = 0.0;
+        double s = 0.0;
+        for (int i = 0; i <= Ms1; i++) s += Tc[i];
+        const double den = 1.0 + s;
+        for (int i = 0; i <= Ms1; i++) Tc[i] /= den;
+        s = 0.0;
+        for (int i = 0; i <= Ms1; i++) s += Tc[i];
+        Tc[Ms1] = 1.0 - s;
+        for (int i = 0; i <= Ms1; i++) Tc[i] *= par.sumT;
     }
-    for (int i = lane; i < N * BW; i += 32) As[i] = 0.0;
-    for (int i = lane; i < 3 * N; i += 32) cs[i] = 0.0;
-    __syncwarp();
+    __syncthreads();
     // ---- splitToFineT (CPU.hpp:930-944) + forwardP (CPU.hpp:729-747) ----
-    for (int i = lane; i < M; i += 32) {
+    for (int i = tid; i < M; i += 64) {
         const int pl = bv.piece_poly[p0 + i];
-        const double Ti = Tc[pl] / bv.intervals[co0 + pl];
-        bv.T[p0 + i] = Ti;
+        bv.T[p0 + i] = Tc[pl] / bv.intervals[co0 + pl];
         if (i < M - 1) {
             const int k = bv.wp_vert_cnt[p0 + i] - 1;
             const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
@@ -91,162 +159,92 @@ __global__ void __launch_bounds__(32) minco_forward_kernel(BatchView bv, const d
                 qy += V[3 * (a + 1) + 1] * rr;
                 qz += V[3 * (a + 1) + 2] * rr;
             }
-            qx += V[0], qy += V[1], qz += V[2];
-            bv.q[3 * (size_t)(p0 + i) + 0] = qx;
-            bv.q[3 * (size_t)(p0 + i) + 1] = qy;
-            bv.q[3 * (size_t)(p0 + i) + 2] = qz;
-            // junction rows 6i+3 .. 6i+8 of A and the waypoint RHS (CPU.hpp:446-478)
-            const double T1 = Ti, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
-            const int r = 6 * i;
-#define A_(row, col) As[(size_t)(row) * BW + ((col) - (row) + 6)]
-            A_(r + 3, r + 3) = 6.0;
-            A_(r + 3, r + 4) = 24.0 * T1;
-            A_(r + 3, r + 5) = 60.0 * T2;
-            A_(r + 3, r + 9) = -6.0;
-            A_(r + 4, r + 4) = 24.0;
-            A_(r + 4, r + 5) = 120.0 * T1;
-            A_(r + 4, r + 10) = -24.0;
-            A_(r + 5, r) = 1.0;
-            A_(r + 5, r + 1) = T1;
-            A_(r + 5, r + 2) = T2;
-            A_(r + 5, r + 3) = T3;
-            A_(r + 5, r + 4) = T4;
-            A_(r + 5, r + 5) = T5;
-            A_(r + 6, r) = 1.0;
-            A_(r + 6, r + 1) = T1;
-            A_(r + 6, r + 2) = T2;
-            A_(r + 6, r + 3) = T3;
-            A_(r + 6, r + 4) = T4;
-            A_(r + 6, r + 5) = T5;
-            A_(r + 6, r + 6) = -1.0;
-            A_(r + 7, r + 1) = 1.0;
-            A_(r + 7, r + 2) = 2 * T1;
-            A_(r + 7, r + 3) = 3 * T2;
-            A_(r + 7, r + 4) = 4 * T3;
-            A_(r + 7, r + 5) = 5 * T4;
-            A_(r + 7, r + 7) = -1.0;
-            A_(r + 8, r + 2) = 2.0;
-            A_(r + 8, r + 3) = 6 * T1;
-            A_(r + 8, r + 4) = 12 * T2;
-            A_(r + 8, r + 5) = 20 * T3;
-            A_(r + 8, r + 8) = -2.0;
-            cs[3 * (r + 5) + 0] = qx;
-            cs[3 * (r + 5) + 1] = qy;
-            cs[3 * (r + 5) + 2] = qz;
-        } else {
-            // last piece: tail rows (CPU.hpp:481-499) and, by the same lane, the head rows (:437-442)
-            const double T1 = Ti, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
-            const int e = N;
-            A_(e - 3, e - 6) = 1.0;
-            A_(e - 3, e - 5) = T1;
-            A_(e - 3, e - 4) = T2;
-            A_(e - 3, e - 3) = T3;
-            A_(e - 3, e - 2) = T4;
-            A_(e - 3, e - 1) = T5;
-            A_(e - 2, e - 5) = 1.0;
-            A_(e - 2, e - 4) = 2 * T1;
-            A_(e - 2, e - 3) = 3 * T2;
-            A_(e - 2, e - 2) = 4 * T3;
-            A_(e - 2, e - 1) = 5 * T4;
-            A_(e - 1, e - 4) = 2;
-            A_(e - 1, e - 3) = 6 * T1;
-            A_(e - 1, e - 2) = 12 * T2;
-            A_(e - 1, e - 1) = 20 * T3;
-            A_(0, 0) = 1.0;
-            A_(1, 1) = 1.0;
-            A_(2, 2) = 2.0;
-            const double* ht = bv.headtail + 18 * (size_t)b;
-            for (int d = 0; d < 3; d++) {
-                cs[0 + d] = ht[0 + d];
-                cs[3 + d] = ht[3 + d];
-                cs[6 + d] = ht[6 + d];
-                cs[3 * (e - 3) + d] = ht[9 + 0 + d];
-                cs[3 * (e - 2) + d] = ht[9 + 3 + d];
-                cs[3 * (e - 1) + d] = ht[9 + 6 + d];
-            }
-#undef A_
+            bv.q[3 * (size_t)(p0 + i) + 0] = qx + V[0];
+            bv.q[3 * (size_t)(p0 + i) + 1] = qy + V[1];
+            bv.q[3 * (size_t)(p0 + i) + 2] = qz + V[2];
         }
     }
-    __syncwarp();
+    __syncthreads();  // T and q (global) are read back by warp 1 below
+    CLK(1);
 
-    // ---- banded LU without pivoting (trajectory.hpp:655-687).  Pivot k updates the 6x6 block below /
-    //      right of it: 6 row groups x 3 lanes, 2 columns per lane.  One barrier per pivot: the
-    //      multiplier l_ik overwrites a_ik one step LATER (nobody reads column k after step k), and the
-    //      lane that produces the next pivot also stores its reciprocal (slot 13), so that the chain per
-    //      pivot is LDS -> MUL -> FMA -> RCP -> STS.  a*(1/b) instead of a/b: <= 1 ulp, inside the stated
-    //      tolerance.  The reference's skip-exact-zero tests only skip arithmetic that changes nothing.
-    {
-        const int r = lane / 3, cg = lane - 3 * r;
-        const bool act = lane < 18;
-        const int s0 = 2 * cg, s1 = 2 * cg + 1;
-        if (lane == 0) As[13] = 1.0 / As[6];
-        __syncwarp();
-        double l_pend = 0.0;
-        int l_addr = -1;
-        for (int k = 0; k <= N - 2; k++) {
-            const int i = k + 1 + r;
-            const bool on = act && i < N;
-            double l = 0.0, v0 = 0.0, v1 = 0.0;
-            if (on) {
-                const double* rk = As + (size_t)k * BW;
-                double* ri = As + (size_t)i * BW;
-                l = ri[5 - r] * rk[13];
-                v0 = ri[6 + s0 - r] - l * rk[7 + s0];
-                v1 = ri[6 + s1 - r] - l * rk[7 + s1];
-                ri[6 + s0 - r] = v0;
-                ri[6 + s1 - r] = v1;
-                if (lane == 0) ri[13] = 1.0 / v0;  // r == 0, s0 == 0: the new diagonal a_{k+1,k+1}
-            }
-            if (l_addr >= 0) As[l_addr] = l_pend;
-            l_addr = (on && cg == 0) ? (i * BW + (5 - r)) : -1;
-            l_pend = l;
-            __syncwarp();
-        }
-        if (l_addr >= 0) As[l_addr] = l_pend;
-        __syncwarp();
+    double* lug = bv.lu + (size_t)BW * 6 * p0;
+    // ---- ring prologue: head rows, junction 0 (or the tail if M == 1), junction 1 ----
+    if (warp == 0) {
+        fill_block(ring, bv, b, p0, M, -1, lane);
+        fill_block(ring, bv, b, p0, M, 0, lane);
+    } else {
+        fill_block(ring, bv, b, p0, M, 1, lane);
     }
-    // ---- forward substitution L y = b (trajectory.hpp:695-705) and back substitution U x = y
-    //      (:706-717), row-oriented with the last six results in a register window: lane d < 3 owns
-    //      right-hand side d; per row the dependent chain is one FMA (+ one MUL by the stored reciprocal
-    //      of the diagonal), everything else streams from shared memory.  The update order per element is
-    //      the reference's (ascending j forward, descending j backward).
-    if (lane < 3) {
-        const int d = lane;
-        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int base = 0; base < N; base += 6) {
-#pragma unroll
-            for (int u = 0; u < 6; u++) {
-                const int i = base + u;
-                const double* Li = As + (size_t)i * BW;
-                double acc = cs[3 * i + d];
-#pragma unroll
-                for (int s = 0; s < 6; s++) acc -= Li[s] * w[(u + s) % 6];
-                w[u] = acc;
-                cs[3 * i + d] = acc;
+    __syncthreads();
+    if (tid == 0) ring[6] = 1.0 / ring[6];
+    __syncthreads();
+    CLK(2);
+    long long busy = 0;
+
+    // ---- phases: piece j = pivots 6j .. 6j+5 ----
+    const int r = lane / 3, cg = lane - 3 * r;
+    const bool act = lane < 18;
+    double l_pend = 0.0;
+    int l_addr = -1;
+    for (int j = 0; j < M; j++) {
+        const long long tb0 = clock64();
+        if (warp == 0) {
+            const int kend = min(6 * j + 6, N - 1);
+            for (int k = 6 * j; k < kend; k++) {
+                const int i = k + 1 + r;
+                const bool on = act && i < N;
+                double l = 0.0;
+                if (on) {
+                    const double* rk = ring + (k & (RING - 1)) * BW;
+                    double* ri = ring + (i & (RING - 1)) * BW;
+                    l = ri[5 - r] * rk[6];  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
+                    const double v0 = ri[6 + cg - r] - l * rk[7 + cg];
+                    const double v1 = ri[9 + cg - r] - l * rk[10 + cg];
+                    const double v2 = ri[13 + cg] - l * rk[13 + cg];
+                    ri[6 + cg - r] = (lane == 0) ? 1.0 / v0 : v0;  // lane 0 (r = 0, cg = 0) owns the next pivot
+                    ri[9 + cg - r] = v1;
+                    ri[13 + cg] = v2;
+                }
+                if (l_addr >= 0) ring[l_addr] = l_pend;  // multiplier of the PREVIOUS step (nobody reads column k-1 any more)
+                l_addr = (on && cg == 0) ? ((i & (RING - 1)) * BW + (5 - r)) : -1;
+                l_pend = l;
+                __syncwarp();
             }
+            if (j == M - 1 && l_addr >= 0) ring[l_addr] = l_pend;
+        } else {
+            if (j >= 1) retire_rows(ring, lug, ust, 6 * (j - 1), 6, lane);
+            fill_block(ring, bv, b, p0, M, j + 2, lane);
         }
-#pragma unroll
-        for (int u = 0; u < 6; u++) w[u] = 0.0;
+        busy += clock64() - tb0;
+        __syncthreads();
+    }
+    CLK(3);
+    if (blockIdx.x == 0 && lane == 0) g_clk[8 + 16 * warp] = busy;
+    // ---- retire the last six rows ----
+    if (warp == 1) retire_rows(ring, lug, ust, 6 * (M - 1), 6, lane);
+    __syncthreads();
+    CLK(4);
+
+    // ---- back substitution U x = y (trajectory.hpp:706-717), row-oriented: lane d < 3 of warp 0 owns
+    //      right-hand side d and keeps the last six results in registers ----
+    if (warp == 0 && lane < 3) {
+        const int d = lane;
+        double* cg_ = bv.c + 18 * (size_t)p0;
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int base = N - 6; base >= 0; base -= 6) {
 #pragma unroll
             for (int u = 5; u >= 0; u--) {
                 const int i = base + u;
-                const double* Ui = As + (size_t)i * BW;
-                double acc = cs[3 * i + d];
+                const double* Ui = ust + (size_t)i * UST;
+                double acc = Ui[6 + d];
 #pragma unroll
-                for (int t = 6; t >= 1; t--) acc -= Ui[6 + t] * w[(u + t) % 6];
-                const double xi = acc * Ui[13];
-                w[u] = xi;
-                cs[3 * i + d] = xi;
+                for (int t = 6; t >= 1; t--) acc -= Ui[t - 1] * w[(u + t) % 6];
+                w[u] = acc;
+                cg_[3 * i + d] = acc;
             }
         }
     }
-    __syncwarp();
-    // ---- write c (6M x 3 row-major == per-piece 6x3 blocks) and the LU factors ----
-    double* cg_ = bv.c + 18 * (size_t)p0;
-    for (int i = lane; i < 3 * N; i += 32) cg_[i] = cs[i];
-    double* lug = bv.lu + (size_t)BW * 6 * p0;
-    for (int i = lane; i < N * BW; i += 32) lug[i] = As[i];
+    CLK(5);
 }
 
 // K2 ---------------------------------------------------------------------------------------------
@@ -512,14 +510,42 @@ __global__ void __launch_bounds__(PEN_THREADS, 2) penalty_kernel(BatchView bv, P
 }
 
 // K3 ---------------------------------------------------------------------------------------------
-// smem: As[N][16] (LU factors, slot 13 = 1/diag) | Bs[N][3] (adjoint RHS -> lambda) | gT[M] | gq[3*M] | Tc-grad[coarseN]
-__global__ void __launch_bounds__(32)
+// One trajectory per CTA of two warps.  The LU factors written by K1 (bv.lu, 16 doubles per row) are
+// streamed through a ring of six 6-row blocks in shared memory: warp 1 issues cp.async copies four
+// blocks ahead of the sweep, warp 0 (lane d < 3 = right-hand side d) runs the two triangular sweeps of
+// A^T lambda = dJ/dc (trajectory.hpp:724-751) row by row with the last six results in registers.
+// Because a block is exactly one piece (6 rows), every shared-memory address of the sweeps is
+// "block base + compile-time offset".  ~16 KB of shared memory per trajectory: the whole batch is resident.
+// smem: ring[6 blocks][6 rows][16] | Bs[N][3] (adjoint RHS -> lambda) | gT[M] | gq[3*M] | gTc[coarseN]
+#define NBLK 6
+#define BLKD (6 * BW)  // doubles per block
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
+}
+// Issue the copy of block `blk` (rows 6*blk .. 6*blk+5) into its ring slot; blocks outside [0, M) are skipped.
+__device__ __forceinline__ void issue_block(double* ring, const double* lug, int blk, int M, int lane) {
+    if (blk >= 0 && blk < M) {
+        double* dst = ring + (size_t)(blk % NBLK) * BLKD;
+        const double* src = lug + (size_t)blk * BLKD;
+        for (int e = lane; e < BLKD / 2; e += 32) cp_async16(dst + 2 * e, src + 2 * e);  // 48 x 16 B
+    }
+}
+
+__global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
     if (bv.active && !bv.active[b]) return;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
     const int M = bv.piece_off[b + 1] - p0;
     const int N = 6 * M;
@@ -529,57 +555,91 @@ __global__ void __launch_bounds__(32)
     const double* x = xin + bv.x_off[b];
     double* grad = grad_out + bv.x_off[b];
     const int dimT = bv.dimT[b];
-    double* As = sm;
-    double* Bs = As + (size_t)N * BW;
+    double* ring = sm;
+    double* Bs = ring + NBLK * BLKD;
     double* gT = Bs + (size_t)3 * N;
     double* gq = gT + M;
     double* gTc = gq + 3 * (size_t)M;
 
     const double* lug = bv.lu + (size_t)BW * 6 * p0;
-    for (int i = lane; i < N * BW; i += 32) As[i] = lug[i];
-    __syncwarp();
-    const double* gdC = bv.gdC + 18 * (size_t)p0;
-    for (int i = lane; i < 3 * N; i += 32) Bs[i] = gdC[i];
-    __syncwarp();
+    // ---- prologue: blocks 0..3 in flight, block -1 (rows -6..-1) = zeros, right-hand side into Bs ----
+    if (warp == 1) {
+        for (int e = lane; e < BLKD; e += 32) ring[(size_t)(NBLK - 1) * BLKD + e] = 0.0;
+        for (int blk = 0; blk < 4; blk++) issue_block(ring, lug, blk, M, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        const double* gdC = bv.gdC + 18 * (size_t)p0;
+        for (int i = lane; i < 3 * N; i += 32) Bs[i] = gdC[i];
+    }
+    __syncthreads();
 
-    // ---- A^T lambda = gdC (trajectory.hpp:724-751): U^T z = b forward, then L^T lambda = z backward,
-    //      row-oriented with a six-entry register window per right-hand side (lane d < 3), in the
-    //      reference's update order (ascending j in the first sweep, descending j in the second).
-    if (lane < 3) {
-        const int d = lane;
-        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int base = 0; base < N; base += 6) {
+    // ---- sweep 1: U^T z = b, ascending rows.  Phase p = rows 6p..6p+5 reads blocks p-1 and p. ----
+    {
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // z_{i-6..i-1} of this lane's right-hand side
+        for (int p = 0; p < M; p++) {
+            if (warp == 1) {
+                issue_block(ring, lug, p + 4, M, lane);  // into the slot of block p-2 (dead)
+                cp_async_commit();
+                cp_async_wait<3>();  // block p+1 has landed
+            } else if (lane < 3) {
+                const int d = lane;
+                const double* cur = ring + (size_t)(p % NBLK) * BLKD;
+                const double* prv = ring + (size_t)((p + NBLK - 1) % NBLK) * BLKD;
+                double* bs = Bs + 18 * (size_t)p + d;
 #pragma unroll
-            for (int u = 0; u < 6; u++) {
-                const int i = base + u;
-                double acc = Bs[3 * i + d];
+                for (int u = 0; u < 6; u++) {
+                    double acc = bs[3 * u];
 #pragma unroll
-                for (int s = 6; s >= 1; s--)
-                    if (i >= s) acc -= As[(size_t)(i - s) * BW + 6 + s] * w[(u - s + 6) % 6];  // u_{i-s,i}
-                const double z = acc * As[(size_t)i * BW + 13];
-                w[u] = z;
-                Bs[3 * i + d] = z;
+                    for (int s = 6; s >= 1; s--) {  // u_{i-s,i} = row (i-s), slot 6+s ; ascending j = i-s
+                        const double coef = (u - s >= 0) ? cur[(u - s) * BW + 6 + s] : prv[(u - s + 6) * BW + 6 + s];
+                        acc -= coef * w[(u - s + 6) % 6];
+                    }
+                    const double z = acc * cur[u * BW + 6];
+                    w[u] = z;
+                    bs[3 * u] = z;
+                }
             }
-        }
-#pragma unroll
-        for (int u = 0; u < 6; u++) w[u] = 0.0;
-        for (int base = N - 6; base >= 0; base -= 6) {
-#pragma unroll
-            for (int u = 5; u >= 0; u--) {
-                const int i = base + u;
-                double acc = Bs[3 * i + d];
-#pragma unroll
-                for (int t = 6; t >= 1; t--)
-                    if (i + t < N) acc -= As[(size_t)(i + t) * BW + (6 - t)] * w[(u + t) % 6];  // l_{i+t,i}
-                w[u] = acc;
-                Bs[3 * i + d] = acc;
-            }
+            __syncthreads();
         }
     }
-    __syncwarp();
+    // ---- transition: the ring now holds blocks M-6..M-1; block M (rows >= N) must read as zeros ----
+    if (warp == 1) {
+        cp_async_wait<0>();
+        for (int e = lane; e < BLKD; e += 32) ring[(size_t)(M % NBLK) * BLKD + e] = 0.0;
+    }
+    __syncthreads();
+    // ---- sweep 2: L^T lambda = z, descending rows.  Phase p = rows 6p+5..6p reads blocks p and p+1. ----
+    {
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // lambda_{i+1..i+6}
+        for (int p = M - 1; p >= 0; p--) {
+            if (warp == 1) {
+                issue_block(ring, lug, p - 4, M, lane);  // into the slot of block p+2 (dead: the sweep reads p and p+1)
+                cp_async_commit();
+                cp_async_wait<3>();  // block p-1 has landed
+            } else if (lane < 3) {
+                const int d = lane;
+                const double* cur = ring + (size_t)(p % NBLK) * BLKD;
+                const double* nxt = ring + (size_t)((p + 1) % NBLK) * BLKD;
+                double* bs = Bs + 18 * (size_t)p + d;
+#pragma unroll
+                for (int u = 5; u >= 0; u--) {
+                    double acc = bs[3 * u];
+#pragma unroll
+                    for (int t = 6; t >= 1; t--) {  // l_{i+t,i} = row (i+t), slot 6-t ; descending j = i+t
+                        const double coef = (u + t < 6) ? cur[(u + t) * BW + 6 - t] : nxt[(u + t - 6) * BW + 6 - t];
+                        acc -= coef * w[(u + t) % 6];
+                    }
+                    w[u] = acc;
+                    bs[3 * u] = acc;
+                }
+            }
+            __syncthreads();
+        }
+    }
     // ---- addPropCtoT (CPU.hpp:104-151), addPropCtoP (:154-161), rho (:989) ----
     const double* cg_ = bv.c + 18 * (size_t)p0;
-    for (int i = lane; i < M; i += 32) {
+    for (int i = tid; i < M; i += 64) {
         const double T1 = bv.T[p0 + i], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2;
         const double* c = cg_ + 18 * i;
         double s = 0.0;
@@ -604,9 +664,9 @@ __global__ void __launch_bounds__(32)
         if (i < M - 1)
             for (int d = 0; d < 3; d++) gq[3 * i + d] = Bs[3 * (6 * i + 5) + d];
     }
-    __syncwarp();
+    __syncthreads();
     // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope ----
-    if (lane == 0) {
+    if (tid == 0) {
         int offset = 0;
         for (int i = 0; i < coarseN; i++) {
             const int iv = bv.intervals[co0 + i];
@@ -616,10 +676,10 @@ __global__ void __launch_bounds__(32)
             offset += iv;
         }
     }
-    __syncwarp();
+    __syncthreads();
     // ---- addLayerTGrad (CPU.hpp:816-894) ----
     if (par.softT) {
-        for (int i = lane; i < dimT; i += 32) {
+        for (int i = tid; i < dimT; i += 64) {
             const double t = x[i];
             double g = gTc[i];
             if (par.c2) {
@@ -633,7 +693,7 @@ __global__ void __launch_bounds__(32)
                 g *= exp(t);
             grad[i] = g;
         }
-    } else if (lane == 0) {
+    } else if (tid == 0) {
         const int Ms1 = dimT;
         const double gTail = par.sumT * gTc[Ms1];
         double expTauSum = 0.0, gFreeDotExpTau = 0.0;
@@ -669,7 +729,7 @@ __global__ void __launch_bounds__(32)
         }
     }
     // ---- addLayerPGrad (CPU.hpp:897-928) ----
-    for (int i = lane; i < M - 1; i += 32) {
+    for (int i = tid; i < M - 1; i += 64) {
         const int k = bv.wp_vert_cnt[p0 + i] - 1;
         const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
         const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
@@ -691,7 +751,7 @@ __global__ void __launch_bounds__(32)
         }
     }
     // ---- cost = jerk energy + penalty + rho * sum(T) (CPU.hpp:542,406,988), sequential sums ----
-    if (lane == 0) {
+    if (tid == 63) {
         double e = 0.0, pn = 0.0;
         for (int i = 0; i < M; i++) e += bv.energy[p0 + i];
         for (int i = 0; i < M; i++) pn += bv.pen[p0 + i];
@@ -710,8 +770,11 @@ __global__ void __launch_bounds__(32)
 // ------------------------------------------------------------------------------------------------
 // Host-side launchers
 // ------------------------------------------------------------------------------------------------
-size_t forward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)18 * M + coarseN + 1); }
-size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)6 * M * BW + (size_t)18 * M + (size_t)4 * M + coarseN + 1); }
+size_t forward_smem_bytes(int M, int coarseN) {
+    const size_t ust = (size_t)6 * M * UST, tc = (size_t)coarseN + 1;
+    return sizeof(double) * ((size_t)RING * BW + (ust > tc ? ust : tc));
+}
+size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1); }
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
     PenaltyLaunch pl;
@@ -745,9 +808,9 @@ cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem)
 
 cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
-    minco_forward_kernel<<<bv.B, 32, fwd_smem, st>>>(bv, x_dev);
+    minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bv, x_dev);
     penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
-    minco_backward_kernel<<<bv.B, 32, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+    minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
     return cudaGetLastError();
 }
 
@@ -762,11 +825,11 @@ cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fw
     cudaError_t err = cudaSuccess;
     for (int r = 0; r < reps && err == cudaSuccess; r++) {
         cudaEventRecord(ev[0], st);
-        minco_forward_kernel<<<bv.B, 32, fwd_smem, st>>>(bv, x_dev);
+        minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bv, x_dev);
         cudaEventRecord(ev[1], st);
         penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
         cudaEventRecord(ev[2], st);
-        minco_backward_kernel<<<bv.B, 32, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+        minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
         cudaEventRecord(ev[3], st);
         err = cudaStreamSynchronize(st);
         for (int k = 0; k < 3 && err == cudaSuccess; k++) {
@@ -789,6 +852,7 @@ __global__ void dfma_peak_kernel(double* out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+void fetch_debug_clocks(long long* out) { cudaMemcpyFromSymbol(out, g_clk, sizeof(long long) * 32); }
 double measure_fp64_tflops() {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
