@@ -1,0 +1,266 @@
+// se3gcopter_b200.hpp — header-only C++ façade over the C ABI (frx.h) with the method set of the
+// reference's optimiser, so that its caller compiles against it unchanged in shape:
+//
+//   reference                                                        this header
+//   ---------------------------------------------------------------  ------------------------------------
+//   class SE3GCOPTER            se3gcopter_cpu.hpp:567                frx::SE3GCOPTER
+//     bool   setup(rho, totalT, iniState, finState, hPolys, gridRes,   same argument order and meaning
+//                  itgSpaces, horizHalfLen, vertHalfLen, margin, vMax,
+//                  minThrAcc, maxThrAcc, bodyRateMax, g, w, c2diffeo)   :1076-1092
+//     double optimize(Trajectory& traj, relCostTol)                    :1230-1268 (returns the jerk cost)
+//     void   kill_kernel()                 se3gcopter_gpu.hpp:907-909   no-op (nothing spins on the device)
+//   class Piece / Trajectory    trajectory.hpp:43, :317               frx::Piece / frx::Trajectory
+//     getPieceNum, getTotalDuration, operator[], getDuration, getOrder, getCoeffMat (3x6, highest order
+//     first), normalizePosCoeffMat, getPos/getVel/getAcc/getJer, getRotation, getTiltRate
+//   caller: MavGlobalPlanner::plan   MinCoPlan_CPU.cpp:114-124, MinCoPlan_GPU.cpp:127
+//
+// Matrices cross this façade as plain column-major arrays (Mat3 = double[9] [p v a]; an H-polytope is a
+// std::vector<double> of 6*F values = the columns of the reference's 6xF matrix).  When Eigen is present at
+// the integrator's site (`__has_include(<Eigen/Eigen>)`), overloads taking Eigen::MatrixXd /
+// std::vector<Eigen::MatrixXd> / Eigen::Vector4d with the reference's exact signature are enabled.
+//
+// Batch extension (not in the reference, which optimises one trajectory per call): frx::SE3GCOPTERBatch
+// solves many candidate trajectories at once and returns the arg-min.
+#pragma once
+#include <array>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "frx.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Eigen>)
+#include <Eigen/Eigen>
+#define FRX_HAVE_EIGEN 1
+#endif
+#endif
+
+namespace frx {
+
+// ---- trajectory containers (trajectory.hpp:43-145, 317-593) -------------------------------------
+class Piece {
+    double duration = 0.0;
+    std::array<double, 18> c{};  // 3x6 column-major, highest order first (trajectory.hpp:39)
+
+public:
+    Piece() = default;
+    Piece(double dur, const double* coeff18) : duration(dur) {
+        for (int i = 0; i < 18; i++) c[i] = coeff18[i];
+    }
+    int getDim() const { return 3; }
+    int getOrder() const { return 5; }
+    double getDuration() const { return duration; }
+    const std::array<double, 18>& getCoeffMat() const { return c; }
+    double coeff(int dim, int col) const { return c[3 * col + dim]; }
+    // trajectory.hpp:75-133
+    std::array<double, 3> getPos(double t) const { return eval(t, 0); }
+    std::array<double, 3> getVel(double t) const { return eval(t, 1); }
+    std::array<double, 3> getAcc(double t) const { return eval(t, 2); }
+    std::array<double, 3> getJer(double t) const { return eval(t, 3); }
+    // trajectory.hpp:135-145: coefficients of the duration-normalised polynomial (wire format of traj2msg)
+    std::array<double, 18> normalizePosCoeffMat() const {
+        std::array<double, 18> n{};
+        double t = 1.0;
+        for (int i = 5; i >= 0; i--) {
+            for (int d = 0; d < 3; d++) n[3 * i + d] = c[3 * i + d] * t;
+            t *= duration;
+        }
+        return n;
+    }
+
+private:
+    std::array<double, 3> eval(double t, int deriv) const {
+        std::array<double, 3> out{0.0, 0.0, 0.0};
+        double tn = 1.0;
+        for (int i = 5 - deriv; i >= 0; i--) {  // column i has power p = 5 - i
+            const int p = 5 - i;
+            double f = 1.0;
+            for (int q = 0; q < deriv; q++) f *= (double)(p - q);
+            for (int d = 0; d < 3; d++) out[d] += f * tn * c[3 * i + d];
+            tn *= t;
+        }
+        return out;
+    }
+};
+
+class Trajectory {
+    std::vector<Piece> pieces;
+
+public:
+    int getPieceNum() const { return (int)pieces.size(); }
+    double getTotalDuration() const {
+        double s = 0.0;
+        for (const auto& p : pieces) s += p.getDuration();
+        return s;
+    }
+    std::vector<double> getDurations() const {
+        std::vector<double> d;
+        for (const auto& p : pieces) d.push_back(p.getDuration());
+        return d;
+    }
+    const Piece& operator[](int i) const { return pieces[i]; }
+    Piece& operator[](int i) { return pieces[i]; }
+    void clear() { pieces.clear(); }
+    void reserve(int n) { pieces.reserve(n); }
+    void emplace_back(double dur, const double* coeff18) { pieces.emplace_back(dur, coeff18); }
+    std::vector<Piece>::const_iterator begin() const { return pieces.begin(); }
+    std::vector<Piece>::const_iterator end() const { return pieces.end(); }
+    // trajectory.hpp:437-455
+    int locatePieceIdx(double& t) const {
+        const int N = getPieceNum();
+        int idx = 0;
+        double dur = 0.0;
+        for (; idx < N && t > (dur = pieces[idx].getDuration()); idx++) t -= dur;
+        if (idx == N) {
+            idx--;
+            t += pieces[idx].getDuration();
+        }
+        return idx;
+    }
+    std::array<double, 3> getPos(double t) const { const int i = locatePieceIdx(t); return pieces[i].getPos(t); }
+    std::array<double, 3> getVel(double t) const { const int i = locatePieceIdx(t); return pieces[i].getVel(t); }
+    std::array<double, 3> getAcc(double t) const { const int i = locatePieceIdx(t); return pieces[i].getAcc(t); }
+    std::array<double, 3> getJer(double t) const { const int i = locatePieceIdx(t); return pieces[i].getJer(t); }
+    // trajectory.hpp:579-592
+    std::array<double, 3> getTiltRate(double t, double gAcc) const {
+        auto a = getAcc(t);
+        a[2] += gAcc;
+        const double thr = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        const double z[3] = {a[0] / thr, a[1] / thr, a[2] / thr};
+        double y[3] = {0.0, z[2], -z[1]};  // z x e_x
+        const double yn = std::sqrt(y[1] * y[1] + y[2] * y[2]);
+        y[1] /= yn, y[2] /= yn;
+        const double xb[3] = {y[1] * z[2] - y[2] * z[1], y[2] * z[0], -y[1] * z[0]};
+        const auto j = getJer(t);
+        const double b0 = (xb[0] * j[0] + xb[1] * j[1] + xb[2] * j[2]) / thr;
+        const double b1 = (y[1] * j[1] + y[2] * j[2]) / thr;
+        return {-b1, b0, 0.0};
+    }
+    // Sampled maxima of |vel| / |acc| (the reference isolates polynomial roots, trajectory.hpp:177-273 via
+    // root_finder.hpp; dense sampling is used here for the printed report only, MinCoPlan_CPU.cpp:131-132).
+    double getMaxVelRate(int samples_per_piece = 256) const { return maxRate(1, samples_per_piece); }
+    double getMaxAccRate(int samples_per_piece = 256) const { return maxRate(2, samples_per_piece); }
+
+private:
+    double maxRate(int deriv, int n) const {
+        double m = 0.0;
+        for (const auto& p : pieces)
+            for (int k = 0; k <= n; k++) {
+                const double t = p.getDuration() * k / n;
+                const auto v = deriv == 1 ? p.getVel(t) : p.getAcc(t);
+                m = std::max(m, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+            }
+        return m;
+    }
+};
+
+// ---- the optimiser --------------------------------------------------------------------------------
+class SE3GCOPTER {
+    frx_batch* h = nullptr;
+    int last_status_ = 0;
+
+public:
+    SE3GCOPTER() = default;
+    SE3GCOPTER(const SE3GCOPTER&) = delete;
+    SE3GCOPTER& operator=(const SE3GCOPTER&) = delete;
+    ~SE3GCOPTER() { frx_batch_destroy(h); }
+
+    // se3gcopter_cpu.hpp:1076-1092.  iniState / finState: 3x3 column-major [p v a]; cfgPolyHs[i]: 6*F_i values
+    // (column k = (outer normal, point) of face k); w = penalty weights (P, V, T, B).
+    // Returns false exactly where the reference does: a polytope or a consecutive intersection with empty
+    // interior (se3gcopter_cpu.hpp:1118-1121).  Any other failure (no CUDA device, ...) throws.
+    bool setup(const double& rh, const double& st, const double* iniState, const double* finState,
+               const std::vector<std::vector<double>>& cfgPolyHs, const double& gridRes, const int& itgSpaces,
+               const double& horiHalfLen, const double& vertHalfLen, const double& margin, const double& vm,
+               const double& minThrAcc, const double& maxThrAcc, const double& bodyRateMax, const double& g,
+               const double* w, bool c2diffeo) {
+        frx_batch_destroy(h);
+        h = nullptr;
+        frx_problem p{};
+        for (int i = 0; i < 9; i++) p.ini[i] = iniState[i], p.fin[i] = finState[i];
+        std::vector<int> off(1, 0);
+        std::vector<double> faces;
+        for (const auto& hp : cfgPolyHs) {
+            faces.insert(faces.end(), hp.begin(), hp.end());
+            off.push_back((int)(faces.size() / 6));
+        }
+        p.n_poly = (int)cfgPolyHs.size();
+        p.face_off = off.data();
+        p.faces = faces.data();
+        p.params = frx_params{rh, st, gridRes, itgSpaces, c2diffeo ? 1 : 0, horiHalfLen, vertHalfLen, margin, vm,
+                              minThrAcc, maxThrAcc, bodyRateMax, g, {w[0], w[1], w[2], w[3]}};
+        const int s = frx_batch_create(&p, 1, -1, &h);
+        if (s == FRX_ERR_INFEASIBLE_GEOMETRY) return false;
+        if (s != FRX_OK) throw std::runtime_error(std::string("SE3GCOPTER::setup: ") + frx_strerror(s));
+        return true;
+    }
+
+    // se3gcopter_cpu.hpp:1230-1268: returns the jerk cost of the final trajectory.
+    double optimize(Trajectory& traj, const double& relCostTol) {
+        if (!h) throw std::runtime_error("SE3GCOPTER::optimize before a successful setup");
+        int n = 0, M = 0;
+        frx_batch_dims(h, 0, &n, &M, nullptr, nullptr);
+        std::vector<double> dur(M), co(18 * (size_t)M);
+        double jerk = 0.0;
+        const int s = frx_batch_optimize(h, relCostTol, dur.data(), co.data(), &jerk, nullptr, &last_status_, nullptr,
+                                         nullptr, nullptr);
+        if (s != FRX_OK) throw std::runtime_error(std::string("SE3GCOPTER::optimize: ") + frx_strerror(s));
+        traj.clear();
+        traj.reserve(M);
+        for (int i = 0; i < M; i++) traj.emplace_back(dur[i], &co[18 * (size_t)i]);
+        return jerk;
+    }
+    // The reference discards lbfgs_optimize's return code (se3gcopter_cpu.hpp:1249); it is kept here.
+    int lbfgs_status() const { return last_status_; }
+    void kill_kernel() {}  // se3gcopter_gpu.hpp:907-909: nothing to kill, kept for source compatibility
+
+#ifdef FRX_HAVE_EIGEN
+    bool setup(const double& rh, const double& st, const Eigen::MatrixXd& iniState, const Eigen::MatrixXd& finState,
+               const std::vector<Eigen::MatrixXd>& cfgPolyHs, const double& gridRes, const int& itgSpaces,
+               const double& horiHalfLen, const double& vertHalfLen, const double& margin, const double& vm,
+               const double& minThrAcc, const double& maxThrAcc, const double& bodyRateMax, const double& g,
+               const Eigen::Vector4d& w, bool c2diffeo) {
+        const Eigen::Matrix3d i3 = iniState, f3 = finState;  // column-major
+        std::vector<std::vector<double>> hp;
+        for (const auto& m : cfgPolyHs) hp.emplace_back(m.data(), m.data() + m.size());  // 6 x F column-major
+        return setup(rh, st, i3.data(), f3.data(), hp, gridRes, itgSpaces, horiHalfLen, vertHalfLen, margin, vm,
+                     minThrAcc, maxThrAcc, bodyRateMax, g, w.data(), c2diffeo);
+    }
+#endif
+};
+
+// ---- batch of candidate trajectories (extension) ----------------------------------------------------
+class SE3GCOPTERBatch {
+    frx_batch* h = nullptr;
+
+public:
+    ~SE3GCOPTERBatch() { frx_batch_destroy(h); }
+    // problems: one frx_problem per candidate; device < 0 = current device
+    int setup(const std::vector<frx_problem>& problems, int device = -1) {
+        frx_batch_destroy(h);
+        h = nullptr;
+        return frx_batch_create(problems.data(), (int)problems.size(), device, &h);
+    }
+    // Solves every candidate; returns the index of the cheapest one (penalised objective) and its trajectory.
+    int optimize(double relCostTol, Trajectory& best, double* best_cost = nullptr) {
+        const int B = frx_batch_count(h);
+        std::vector<int> poff(B + 1);
+        frx_batch_piece_offsets(h, poff.data());
+        std::vector<double> dur(poff[B]), co(18 * (size_t)poff[B]);
+        const int s = frx_batch_optimize(h, relCostTol, dur.data(), co.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (s != FRX_OK) return s;
+        int idx = -1;
+        double c = 0.0;
+        const int s2 = frx_batch_argmin(h, &idx, &c);
+        if (s2 != FRX_OK) return s2;
+        best.clear();
+        for (int i = poff[idx]; i < poff[idx + 1]; i++) best.emplace_back(dur[i], &co[18 * (size_t)i]);
+        if (best_cost) *best_cost = c;
+        return idx;
+    }
+    frx_batch* handle() { return h; }
+};
+
+}  // namespace frx
