@@ -46,33 +46,51 @@ __device__ __forceinline__ double c2_forward(double t) {  // CPU.hpp:639-641
 // before) | [7..12] u_{i,i+1..i+6} | [13..15] right-hand side (x,y,z).  Rows are retired to bv.lu in the
 // same layout.
 #define RING 32
-__device__ long long g_clk[32];
-#define CLK(slot) do { if (blockIdx.x == 0 && lane == 0) g_clk[(slot) + 16 * warp] = clock64(); } while (0)
 #define UST 9  // compact store per row, pre-multiplied by 1/u_ii: u_{i,i+1..i+6}/u_ii, y_{x,y,z}/u_ii
 
 // Entry tables of one junction block (rows 6i+3 .. 6i+8, CPU.hpp:446-476): value = coef * T^pow at
 // (row offset, band slot = column - row + 6).
-__constant__ int JR[31] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
-__constant__ int JS[31] = {6, 7, 8, 12, 6, 7, 12, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 6, 0, 1, 2, 3, 6};
-__constant__ double JC[31] = {6.0, 24.0, 60.0, -6.0, 24.0, 120.0, -24.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
+__device__ const int JR[31] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
+__device__ const int JS[31] = {6, 7, 8, 12, 6, 7, 12, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 6, 0, 1, 2, 3, 6};
+__device__ const double JC[31] = {6.0, 24.0, 60.0, -6.0, 24.0, 120.0, -24.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
                               1.0, 1.0, -1.0, 1.0, 2.0, 3.0, 4.0, 5.0, -1.0, 2.0, 6.0, 12.0, 20.0, -2.0};
-__constant__ int JP[31] = {0, 1, 2, 0, 0, 1, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 0};
+__device__ const int JP[31] = {0, 1, 2, 0, 0, 1, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 0};
 // Tail block (rows 6M-3 .. 6M-1, CPU.hpp:481-495), T of the last piece.
-__constant__ int TR[15] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2};
-__constant__ int TS[15] = {3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 3, 4, 5, 6};
-__constant__ double TC[15] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 4.0, 5.0, 2.0, 6.0, 12.0, 20.0};
-__constant__ int TP[15] = {0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3};
+__device__ const int TR[15] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2};
+__device__ const int TS[15] = {3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 3, 4, 5, 6};
+__device__ const double TC[15] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 4.0, 5.0, 2.0, 6.0, 12.0, 20.0};
+__device__ const int TP[15] = {0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3};
 
 __device__ __forceinline__ double pick_pow(int p, double T1, double T2, double T3, double T4, double T5) {
     return p == 0 ? 1.0 : (p == 1 ? T1 : (p == 2 ? T2 : (p == 3 ? T3 : (p == 4 ? T4 : T5))));
 }
+// 1/x without the slow-path branches of the compiler's division: hardware seed + two Newton steps (~1 ulp).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 
-// Fill the rows of block `g` (g = -1: head rows 0..2; 0 <= g <= M-2: junction g; g = M-1: tail rows) into
-// the ring, executed by one full warp (lane = 0..31).
-__device__ __forceinline__ void fill_block(double* ring, const BatchView& bv, int b, int p0, int M, int g, int lane) {
+// CTA-wide barrier usable from warp-specialised branches (both warps of the 64-thread CTA arrive at barrier 1).
+__device__ __forceinline__ void cta_bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+// Per-lane entry of the fill tables (lane e writes entry e of a junction / tail block).
+struct FillLane {
+    int jr, js, jp, tr, ts, tp;
+    double jc, tc;
+};
+
+// Fill the rows of block `g` into the ring, by one full warp.  g = -1: head rows 0..2; 0 <= g <= M-2: junction g
+// (duration Tg, waypoint qv on lanes 0..2); g = M-1: tail rows (duration Tg = T of the last piece); g = M: six zero
+// rows after the matrix (so that the pivot loop needs no bounds predicates).
+__device__ __forceinline__ void fill_block(double* ring, const BatchView& bv, int b, int M, int g, int lane, const FillLane& fl,
+                                           double Tg, double qv) {
     const int N = 6 * M;
-    if (g < -1 || g > M - 1) return;
-    const int row0 = (g < 0) ? 0 : ((g == M - 1) ? N - 3 : 6 * g + 3);
+    if (g < -1 || g > M) return;
+    const int row0 = (g < 0) ? 0 : ((g >= M - 1) ? (g == M ? N : N - 3) : 6 * g + 3);
     const int nrows = (g < 0 || g == M - 1) ? 3 : 6;
     for (int e = lane; e < nrows * BW; e += 32) ring[((row0 + e / BW) & (RING - 1)) * BW + (e % BW)] = 0.0;
     __syncwarp();
@@ -81,13 +99,13 @@ __device__ __forceinline__ void fill_block(double* ring, const BatchView& bv, in
         if (lane < 3) ring[(lane & (RING - 1)) * BW + 6] = (lane == 2) ? 2.0 : 1.0;  // A(0,0)=1, A(1,1)=1, A(2,2)=2
         if (lane < 9) ring[((lane / 3) & (RING - 1)) * BW + 13 + lane % 3] = ht[lane];  // rows 0,1,2 <- head p, v, a
     } else if (g < M - 1) {
-        const double T1 = bv.T[p0 + g], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
-        if (lane < 31) ring[((row0 + JR[lane]) & (RING - 1)) * BW + JS[lane]] = JC[lane] * pick_pow(JP[lane], T1, T2, T3, T4, T5);
-        if (lane < 3) ring[((row0 + 2) & (RING - 1)) * BW + 13 + lane] = bv.q[3 * (size_t)(p0 + g) + lane];  // waypoint row 6g+5
-    } else {
-        const double T1 = bv.T[p0 + M - 1], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        const double T1 = Tg, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        if (lane < 31) ring[((row0 + fl.jr) & (RING - 1)) * BW + fl.js] = fl.jc * pick_pow(fl.jp, T1, T2, T3, T4, T5);
+        if (lane < 3) ring[((row0 + 2) & (RING - 1)) * BW + 13 + lane] = qv;  // waypoint row 6g+5
+    } else if (g == M - 1) {
+        const double T1 = Tg, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
         const double* ht = bv.headtail + 18 * (size_t)b + 9;
-        if (lane < 15) ring[((row0 + TR[lane]) & (RING - 1)) * BW + TS[lane]] = TC[lane] * pick_pow(TP[lane], T1, T2, T3, T4, T5);
+        if (lane < 15) ring[((row0 + fl.tr) & (RING - 1)) * BW + fl.ts] = fl.tc * pick_pow(fl.tp, T1, T2, T3, T4, T5);
         if (lane < 9) ring[((row0 + lane / 3) & (RING - 1)) * BW + 13 + lane % 3] = ht[lane];
     }
     __syncwarp();
@@ -103,7 +121,7 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
     }
 }
 
-// smem: ring[RING][16] | ust[N][10] | Tc[coarseN]
+// smem: ring[RING][16] | scratch[32] | ust[N][9] (aliased by Tc[coarseN] during the prologue)
 __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
     const int b = blockIdx.x;
@@ -119,9 +137,9 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     const double* x = xin + bv.x_off[b];
     const int dimT = bv.dimT[b];
     double* ring = sm;
-    double* ust = ring + RING * BW;
+    double* scratch = ring + RING * BW;
+    double* ust = scratch + 32;
     double* Tc = ust;  // coarse durations: dead before the first row is retired into ust
-    CLK(0);
 
     // ---- forwardT (CPU.hpp:626-676) ----
     if (par.softT) {
@@ -164,66 +182,79 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             bv.q[3 * (size_t)(p0 + i) + 2] = qz + V[2];
         }
     }
-    __syncthreads();  // T and q (global) are read back by warp 1 below
-    CLK(1);
+    __syncthreads();  // T and q (global) are read back below
 
     double* lug = bv.lu + (size_t)BW * 6 * p0;
-    // ---- ring prologue: head rows, junction 0 (or the tail if M == 1), junction 1 ----
+    FillLane fl;
+    {
+        const int e = lane < 31 ? lane : 0, t = lane < 15 ? lane : 0;
+        fl.jr = JR[e], fl.js = JS[e], fl.jp = JP[e], fl.jc = JC[e];
+        fl.tr = TR[t], fl.ts = TS[t], fl.tp = TP[t], fl.tc = TC[t];
+    }
+    auto loadT = [&](int g) { return (g >= 0 && g < M) ? bv.T[p0 + g] : 1.0; };
+    auto loadq = [&](int g) { return (lane < 3 && g >= 0 && g < M - 1) ? bv.q[3 * (size_t)(p0 + g) + lane] : 0.0; };
+    // ---- ring prologue: head rows, block 0, block 1 ----
     if (warp == 0) {
-        fill_block(ring, bv, b, p0, M, -1, lane);
-        fill_block(ring, bv, b, p0, M, 0, lane);
+        fill_block(ring, bv, b, M, -1, lane, fl, 1.0, 0.0);
+        fill_block(ring, bv, b, M, 0, lane, fl, loadT(0), loadq(0));
     } else {
-        fill_block(ring, bv, b, p0, M, 1, lane);
+        fill_block(ring, bv, b, M, 1, lane, fl, loadT(1), loadq(1));
     }
     __syncthreads();
     if (tid == 0) ring[6] = 1.0 / ring[6];
     __syncthreads();
-    CLK(2);
-    long long busy = 0;
 
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
-    const int r = lane / 3, cg = lane - 3 * r;
-    const bool act = lane < 18;
-    double l_pend = 0.0;
-    int l_addr = -1;
-    for (int j = 0; j < M; j++) {
-        const long long tb0 = clock64();
-        if (warp == 0) {
+    if (warp == 0) {
+        const int r = lane / 3, cg = lane - 3 * r;
+        constexpr unsigned RB = RING * BW * 8;  // ring size in bytes (power of two)
+        char* const rb = reinterpret_cast<char*>(ring);
+        unsigned ok = 0;                               // byte offset of pivot row k
+        unsigned oi = ((1 + r) * BW * 8) & (RB - 1);   // byte offset of row k+1+r
+        const unsigned cA = (5 - r) * 8, cB = (6 + cg - r) * 8, cC = (13 + cg) * 8, cK = cg * 8;
+        double* pend = scratch + lane;
+        double l_pend = 0.0;
+        const bool act = lane < 18;
+        for (int j = 0; j < M; j++) {
             const int kend = min(6 * j + 6, N - 1);
             for (int k = 6 * j; k < kend; k++) {
-                const int i = k + 1 + r;
-                const bool on = act && i < N;
-                double l = 0.0;
-                if (on) {
-                    const double* rk = ring + (k & (RING - 1)) * BW;
-                    double* ri = ring + (i & (RING - 1)) * BW;
-                    l = ri[5 - r] * rk[6];  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
-                    const double v0 = ri[6 + cg - r] - l * rk[7 + cg];
-                    const double v1 = ri[9 + cg - r] - l * rk[10 + cg];
-                    const double v2 = ri[13 + cg] - l * rk[13 + cg];
-                    ri[6 + cg - r] = (lane == 0) ? 1.0 / v0 : v0;  // lane 0 (r = 0, cg = 0) owns the next pivot
-                    ri[9 + cg - r] = v1;
-                    ri[13 + cg] = v2;
+                if (act) {
+                    const double* rk = reinterpret_cast<const double*>(rb + ok);
+                    const double* rk2 = reinterpret_cast<const double*>(rb + ok + cK);
+                    double* pa = reinterpret_cast<double*>(rb + oi + cA);
+                    double* pb = reinterpret_cast<double*>(rb + oi + cB);
+                    double* pc = reinterpret_cast<double*>(rb + oi + cC);
+                    const double l = *pa * rk[6];  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
+                    const double v0 = pb[0] - l * rk2[7];
+                    const double v1 = pb[3] - l * rk2[10];
+                    const double v2 = *pc - l * rk2[13];
+                    pb[0] = (lane == 0) ? fast_rcp(v0) : v0;  // lane 0 (r = 0, cg = 0) owns the next pivot: store 1/u
+                    pb[3] = v1;
+                    *pc = v2;
+                    *pend = l_pend;  // multiplier of the PREVIOUS step (nobody reads column k-1 any more)
+                    pend = (cg == 0) ? pa : scratch + lane;
+                    l_pend = l;
                 }
-                if (l_addr >= 0) ring[l_addr] = l_pend;  // multiplier of the PREVIOUS step (nobody reads column k-1 any more)
-                l_addr = (on && cg == 0) ? ((i & (RING - 1)) * BW + (5 - r)) : -1;
-                l_pend = l;
+                ok = (ok + BW * 8) & (RB - 1);
+                oi = (oi + BW * 8) & (RB - 1);
                 __syncwarp();
             }
-            if (j == M - 1 && l_addr >= 0) ring[l_addr] = l_pend;
-        } else {
-            if (j >= 1) retire_rows(ring, lug, ust, 6 * (j - 1), 6, lane);
-            fill_block(ring, bv, b, p0, M, j + 2, lane);
+            if (j == M - 1 && act) *pend = l_pend;
+            cta_bar64();
         }
-        busy += clock64() - tb0;
-        __syncthreads();
+    } else {
+        double Tn = loadT(2), qn = loadq(2);  // operands of the fill of phase 0
+        for (int j = 0; j < M; j++) {
+            const double Tc_ = Tn, qc_ = qn;
+            Tn = loadT(j + 3), qn = loadq(j + 3);  // prefetch for the next phase (latency hidden behind this phase)
+            fill_block(ring, bv, b, M, j + 2, lane, fl, Tc_, qc_);
+            if (j >= 1) retire_rows(ring, lug, ust, 6 * (j - 1), 6, lane);
+            cta_bar64();
+        }
     }
-    CLK(3);
-    if (blockIdx.x == 0 && lane == 0) g_clk[8 + 16 * warp] = busy;
     // ---- retire the last six rows ----
     if (warp == 1) retire_rows(ring, lug, ust, 6 * (M - 1), 6, lane);
     __syncthreads();
-    CLK(4);
 
     // ---- back substitution U x = y (trajectory.hpp:706-717), row-oriented: lane d < 3 of warp 0 owns
     //      right-hand side d and keeps the last six results in registers ----
@@ -244,7 +275,6 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             }
         }
     }
-    CLK(5);
 }
 
 // K2 ---------------------------------------------------------------------------------------------
@@ -259,10 +289,10 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 // Same mathematics as the reference, different association (inside the stated tolerance).
 //
 // smem: cf[ppc][60] derivative coefficient tables | fc[ppc][6*max_faces] | part[20][threads]
-#define PEN_THREADS 256
+#define PEN_THREADS 128
 #define CF 60  // per piece: 18 pos + 15 vel + 12 acc + 9 jerk + 6 snap coefficients
 
-__global__ void __launch_bounds__(PEN_THREADS, 2) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
+__global__ void __launch_bounds__(PEN_THREADS, 4) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int gp_base = blockIdx.x * pl.ppc;
@@ -402,8 +432,11 @@ __global__ void __launch_bounds__(PEN_THREADS, 2) penalty_kernel(BatchView bv, P
                 double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef * e_m * n
                 bool sfc_on = false;
                 for (int k = 0; k < F; k++) {
-                    const double nx = faces[6 * k], ny = faces[6 * k + 1], nz = faces[6 * k + 2];
-                    const double nd = nx * (pos[0] - faces[6 * k + 3]) + ny * (pos[1] - faces[6 * k + 4]) + nz * (pos[2] - faces[6 * k + 5]);
+                    const double2 f01 = *reinterpret_cast<const double2*>(faces + 6 * k);
+                    const double2 f23 = *reinterpret_cast<const double2*>(faces + 6 * k + 2);
+                    const double2 f45 = *reinterpret_cast<const double2*>(faces + 6 * k + 4);
+                    const double nx = f01.x, ny = f01.y, nz = f23.x;
+                    const double nd = nx * (pos[0] - f23.y) + ny * (pos[1] - f45.x) + nz * (pos[2] - f45.y);
                     // |E R^T n| <= emax: faces farther than emax + margin cannot be active
                     if (nd + margin + emax < -1.0e-9) continue;
                     const double ux = (xx * nx + xy * ny + xz * nz) * ex;
@@ -772,7 +805,7 @@ __global__ void __launch_bounds__(64)
 // ------------------------------------------------------------------------------------------------
 size_t forward_smem_bytes(int M, int coarseN) {
     const size_t ust = (size_t)6 * M * UST, tc = (size_t)coarseN + 1;
-    return sizeof(double) * ((size_t)RING * BW + (ust > tc ? ust : tc));
+    return sizeof(double) * ((size_t)RING * BW + 32 + (ust > tc ? ust : tc));
 }
 size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1); }
 
@@ -788,7 +821,7 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
     }
     pl.spt = best_spt;
     pl.tpp = (S + pl.spt - 1) / pl.spt;
-    pl.threads = 256;
+    pl.threads = 128;
     pl.ppc = pl.threads / pl.tpp;
     if (pl.ppc < 1) pl.ppc = 1;
     pl.grid = (bv.total_pieces + pl.ppc - 1) / pl.ppc;
@@ -852,7 +885,6 @@ __global__ void dfma_peak_kernel(double* out, int iters) {
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
-void fetch_debug_clocks(long long* out) { cudaMemcpyFromSymbol(out, g_clk, sizeof(long long) * 32); }
 double measure_fp64_tflops() {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);

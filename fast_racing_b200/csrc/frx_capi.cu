@@ -24,7 +24,6 @@ cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd
 cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                          const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);
 double measure_fp64_tflops();
-void fetch_debug_clocks(long long* out);
 }  // namespace frx
 
 using namespace frx;
@@ -403,7 +402,6 @@ int frx_batch_penalty_launch(const frx_batch* b, long long* out) {
 }
 // Measured fp64 FMA peak (TFLOP/s) of the current device: the secondary roofline of this path.
 double frx_measure_fp64_tflops(void) { return measure_fp64_tflops(); }
-void frx_debug_clocks(long long* out) { fetch_debug_clocks(out); }
 
 // Intermediate device quantities of the last evaluation (for component-level parity tests):
 // T[pieces], q[3*pieces] (last slot unused), c[18*pieces], gdC_lambda[18*pieces], pen[pieces], energy[pieces], gdT[pieces]
