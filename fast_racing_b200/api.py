@@ -143,6 +143,7 @@ def load_library():
         "frx_batch_eval_device": (ci, [vp, vp, vp, vp, vp]),
         "frx_batch_eval_launches": (ci, [vp]),
         "frx_batch_stream": (vp, [vp]),
+        "frx_batch_host_buffers": (ci, [vp, P(P(cd)), P(P(cd)), P(P(cd))]),
         "frx_eval": (cd, [vp, P(cd), P(cd), ci]),
         "frx_batch_optimize": (ci, [vp, cd, P(cd), P(cd), P(cd), P(cd), P(ci), P(ci), P(ci), P(cd)]),
         "frx_batch_argmin": (ci, [vp, P(ci), P(cd)]),
@@ -169,7 +170,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "frx_batch_create", "frx_batch_destroy", "frx_batch_count", "frx_batch_dims", "frx_batch_x_offsets",
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
-    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
+    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version",
 ]
 
@@ -291,6 +292,19 @@ class Batch:
         grad = np.zeros(self.total_x)
         _check(self.lib.frx_batch_eval(self.h, _dp(x), _dp(cost), _dp(grad)), "frx_batch_eval")
         return cost, grad
+
+    def host_buffers(self):
+        """numpy views of the batch's pinned host buffers (x, cost, grad): eval_pinned() transfers straight from/to them."""
+        px, pc, pg = C.POINTER(C.c_double)(), C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        _check(self.lib.frx_batch_host_buffers(self.h, C.byref(px), C.byref(pc), C.byref(pg)), "host_buffers")
+        self._pins = (px, pc, pg)
+        return (np.ctypeslib.as_array(px, shape=(self.total_x,)), np.ctypeslib.as_array(pc, shape=(self.count,)),
+                np.ctypeslib.as_array(pg, shape=(self.total_x,)))
+
+    def eval_pinned(self):
+        """frx_batch_eval on the batch's own pinned buffers (fill host_buffers()[0] first): no staging copies."""
+        px, pc, pg = self._pins
+        _check(self.lib.frx_batch_eval(self.h, px, pc, pg), "frx_batch_eval")
 
     def eval_device(self, x_ptr, cost_ptr, grad_ptr, stream_ptr=0):
         """Device-pointer evaluation on a CUDA stream (integers: data_ptr() / cuda_stream)."""

@@ -167,9 +167,11 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
             const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
             double sn = 0.0;
+#pragma unroll 8
             for (int a = 0; a < k; a++) sn += xi[a] * xi[a];
             const double sc = 2.0 / (1.0 + sn);
             double qx = 0.0, qy = 0.0, qz = 0.0;
+#pragma unroll 4
             for (int a = 0; a < k; a++) {
                 const double r = sc * xi[a];
                 const double rr = r * r;
@@ -544,14 +546,18 @@ __global__ void __launch_bounds__(PEN_THREADS, 4) penalty_kernel(BatchView bv, P
 
 // K3 ---------------------------------------------------------------------------------------------
 // One trajectory per CTA of two warps.  The LU factors written by K1 (bv.lu, 16 doubles per row) are
-// streamed through a ring of six 6-row blocks in shared memory: warp 1 issues cp.async copies four
+// streamed through a ring of 6-row blocks in shared memory: warp 1 issues cp.async copies LOOKAHEAD
 // blocks ahead of the sweep, warp 0 (lane d < 3 = right-hand side d) runs the two triangular sweeps of
 // A^T lambda = dJ/dc (trajectory.hpp:724-751) row by row with the last six results in registers.
 // Because a block is exactly one piece (6 rows), every shared-memory address of the sweeps is
-// "block base + compile-time offset".  ~16 KB of shared memory per trajectory: the whole batch is resident.
-// smem: ring[6 blocks][6 rows][16] | Bs[N][3] (adjoint RHS -> lambda) | gT[M] | gq[3*M] | gTc[coarseN]
-#define NBLK 6
-#define BLKD (6 * BW)  // doubles per block
+// "block base + compile-time offset".  The sweeps are software-pipelined by hand: the part of row u+2
+// that does not depend on row u+1 is issued before row u+1 is finished, so the dependent chain per row is
+// one FMA + one MUL.  While the copies fly, warp 1 also sums the cost (sequential order of the reference),
+// stages the interval table and pulls this trajectory's x / vertex ranges towards L2 for the epilogue.
+// smem: ring[NBLK][6][16] | Bs[N][3] (adjoint RHS -> lambda) | gT[M] | gq[3*M] | gTc[coarseN] | em[2*M] | ivs[coarseN]
+#define NBLK 8
+#define LOOKAHEAD (NBLK - 2)  // blocks in flight ahead of the sweep
+#define BLKD (6 * BW)         // doubles per block
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -562,6 +568,7 @@ template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Issue the copy of block `blk` (rows 6*blk .. 6*blk+5) into its ring slot; blocks outside [0, M) are skipped.
 __device__ __forceinline__ void issue_block(double* ring, const double* lug, int blk, int M, int lane) {
     if (blk >= 0 && blk < M) {
@@ -588,18 +595,56 @@ __global__ void __launch_bounds__(64)
     const double* x = xin + bv.x_off[b];
     double* grad = grad_out + bv.x_off[b];
     const int dimT = bv.dimT[b];
+    const int nx = bv.x_off[b + 1] - bv.x_off[b];
     double* ring = sm;
     double* Bs = ring + NBLK * BLKD;
     double* gT = Bs + (size_t)3 * N;
     double* gq = gT + M;
     double* gTc = gq + 3 * (size_t)M;
+    double* em = gTc + coarseN;
+    int* ivs = reinterpret_cast<int*>(em + 2 * (size_t)M);
 
     const double* lug = bv.lu + (size_t)BW * 6 * p0;
-    // ---- prologue: blocks 0..3 in flight, block -1 (rows -6..-1) = zeros, right-hand side into Bs ----
+    const double* cg_ = bv.c + 18 * (size_t)p0;
+    // epilogue operands of this thread's first piece, requested now so that their latency is hidden
+    double pc[18], pT = 0.0, pgdT = 0.0;
+    if (tid < M) {
+#pragma unroll
+        for (int q = 0; q < 18; q++) pc[q] = cg_[18 * tid + q];
+        pT = bv.T[p0 + tid];
+        pgdT = bv.gdT[p0 + tid];
+    }
+    // ---- prologue ----
     if (warp == 1) {
-        for (int e = lane; e < BLKD; e += 32) ring[(size_t)(NBLK - 1) * BLKD + e] = 0.0;
-        for (int blk = 0; blk < 4; blk++) issue_block(ring, lug, blk, M, lane);
+        for (int e = lane; e < BLKD; e += 32) ring[(size_t)(NBLK - 1) * BLKD + e] = 0.0;  // block -1 (rows -6..-1) = zeros
+        for (int blk = 0; blk < LOOKAHEAD; blk++) issue_block(ring, lug, blk, M, lane);
         cp_async_commit();
+        // while the copies fly: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988), sequential sums
+        for (int i = lane; i < M; i += 32) {
+            em[i] = bv.energy[p0 + i];
+            em[M + i] = bv.pen[p0 + i];
+        }
+        for (int i = lane; i < coarseN; i += 32) ivs[i] = bv.intervals[co0 + i];
+        __syncwarp();
+        if (lane == 0) {
+            double e = 0.0, pn = 0.0;
+            for (int i = 0; i < M; i++) e += em[i];
+            for (int i = 0; i < M; i++) pn += em[M + i];
+            double sT = 0.0;
+            if (par.softT) {
+                for (int i = 0; i < coarseN; i++) sT += par.c2 ? c2_forward(x[i]) : exp(x[i]);
+            } else {
+                for (int i = 0; i < M; i++) sT += bv.T[p0 + i];  // fixed total time: rho = 0 anyway
+            }
+            cost_out[b] = (e + pn) + par.rho * sT;
+        }
+        // pull x and the vertex range of this trajectory towards L2 for addLayerPGrad
+        for (int o = lane * 16; o < nx; o += 32 * 16) prefetch_l2(x + o);
+        if (M > 1) {
+            const double* v0 = bv.verts + 3 * (size_t)bv.wp_vert_off[p0];
+            const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
+            for (const double* q = v0 + lane * 16; q < v1; q += 32 * 16) prefetch_l2(q);
+        }
         cp_async_wait<0>();
     } else {
         const double* gdC = bv.gdC + 18 * (size_t)p0;
@@ -608,78 +653,113 @@ __global__ void __launch_bounds__(64)
     __syncthreads();
 
     // ---- sweep 1: U^T z = b, ascending rows.  Phase p = rows 6p..6p+5 reads blocks p-1 and p. ----
+    // coefficient u_{i-s,i} = row (i-s), slot 6+s; update order = ascending j = i-s, i.e. s = 6..1.
+#define UCOEF(u, s) (((u) - (s) >= 0) ? cur[((u) - (s)) * BW + 6 + (s)] : prv[((u) - (s) + 6) * BW + 6 + (s)])
+#define PRE1(u) (((((bs[3 * (u)] - UCOEF(u, 6) * w[((u) + 0) % 6]) - UCOEF(u, 5) * w[((u) + 1) % 6]) - UCOEF(u, 4) * w[((u) + 2) % 6]) - \
+                  UCOEF(u, 3) * w[((u) + 3) % 6]) - UCOEF(u, 2) * w[((u) + 4) % 6])
+#define FIN1(u, pre) (((pre)-UCOEF(u, 1) * w[((u) + 5) % 6]) * cur[(u) * BW + 6])
     {
-        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // z_{i-6..i-1} of this lane's right-hand side
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // z_{i-6..i-1} of this lane's right-hand side: z_j at w[j mod 6]
         for (int p = 0; p < M; p++) {
             if (warp == 1) {
-                issue_block(ring, lug, p + 4, M, lane);  // into the slot of block p-2 (dead)
+                issue_block(ring, lug, p + LOOKAHEAD, M, lane);  // into the slot of block p-2 (dead)
                 cp_async_commit();
-                cp_async_wait<3>();  // block p+1 has landed
+                cp_async_wait<LOOKAHEAD - 1>();  // block p+1 has landed
             } else if (lane < 3) {
-                const int d = lane;
                 const double* cur = ring + (size_t)(p % NBLK) * BLKD;
                 const double* prv = ring + (size_t)((p + NBLK - 1) % NBLK) * BLKD;
-                double* bs = Bs + 18 * (size_t)p + d;
-#pragma unroll
-                for (int u = 0; u < 6; u++) {
-                    double acc = bs[3 * u];
-#pragma unroll
-                    for (int s = 6; s >= 1; s--) {  // u_{i-s,i} = row (i-s), slot 6+s ; ascending j = i-s
-                        const double coef = (u - s >= 0) ? cur[(u - s) * BW + 6 + s] : prv[(u - s + 6) * BW + 6 + s];
-                        acc -= coef * w[(u - s + 6) % 6];
-                    }
-                    const double z = acc * cur[u * BW + 6];
-                    w[u] = z;
-                    bs[3 * u] = z;
-                }
+                double* bs = Bs + 18 * (size_t)p + lane;
+                // pipelined: PRE(u+2) (needs z_u) is issued before FIN(u+1)
+                double pre0 = PRE1(0);
+                double pre1 = PRE1(1);
+                const double z0 = FIN1(0, pre0);
+                w[0] = z0;
+                double pre2 = PRE1(2);
+                const double z1 = FIN1(1, pre1);
+                w[1] = z1;
+                double pre3 = PRE1(3);
+                const double z2 = FIN1(2, pre2);
+                w[2] = z2;
+                double pre4 = PRE1(4);
+                const double z3 = FIN1(3, pre3);
+                w[3] = z3;
+                double pre5 = PRE1(5);
+                const double z4 = FIN1(4, pre4);
+                w[4] = z4;
+                const double z5 = FIN1(5, pre5);
+                w[5] = z5;
+                bs[0] = z0, bs[3] = z1, bs[6] = z2, bs[9] = z3, bs[12] = z4, bs[15] = z5;
             }
             __syncthreads();
         }
     }
-    // ---- transition: the ring now holds blocks M-6..M-1; block M (rows >= N) must read as zeros ----
+#undef UCOEF
+#undef PRE1
+#undef FIN1
+    // ---- transition: the ring now holds blocks M-NBLK..M-1; block M (rows >= N) must read as zeros ----
     if (warp == 1) {
         cp_async_wait<0>();
         for (int e = lane; e < BLKD; e += 32) ring[(size_t)(M % NBLK) * BLKD + e] = 0.0;
     }
     __syncthreads();
     // ---- sweep 2: L^T lambda = z, descending rows.  Phase p = rows 6p+5..6p reads blocks p and p+1. ----
+    // coefficient l_{i+t,i} = row (i+t), slot 6-t; update order = descending j = i+t, i.e. t = 6..1.
+#define LCOEF(u, t) (((u) + (t) < 6) ? cur[((u) + (t)) * BW + 6 - (t)] : nxt[((u) + (t) - 6) * BW + 6 - (t)])
+#define PRE2(u) (((((bs[3 * (u)] - LCOEF(u, 6) * w[((u) + 6) % 6]) - LCOEF(u, 5) * w[((u) + 5) % 6]) - LCOEF(u, 4) * w[((u) + 4) % 6]) - \
+                  LCOEF(u, 3) * w[((u) + 3) % 6]) - LCOEF(u, 2) * w[((u) + 2) % 6])
+#define FIN2(u, pre) ((pre)-LCOEF(u, 1) * w[((u) + 1) % 6])
     {
-        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // lambda_{i+1..i+6}
+        double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // lambda_{i+1..i+6}: lambda_j at w[j mod 6]
         for (int p = M - 1; p >= 0; p--) {
             if (warp == 1) {
-                issue_block(ring, lug, p - 4, M, lane);  // into the slot of block p+2 (dead: the sweep reads p and p+1)
+                issue_block(ring, lug, p - LOOKAHEAD, M, lane);  // into the slot of block p+2 (dead: the sweep reads p and p+1)
                 cp_async_commit();
-                cp_async_wait<3>();  // block p-1 has landed
+                cp_async_wait<LOOKAHEAD - 1>();  // block p-1 has landed
             } else if (lane < 3) {
-                const int d = lane;
                 const double* cur = ring + (size_t)(p % NBLK) * BLKD;
                 const double* nxt = ring + (size_t)((p + 1) % NBLK) * BLKD;
-                double* bs = Bs + 18 * (size_t)p + d;
-#pragma unroll
-                for (int u = 5; u >= 0; u--) {
-                    double acc = bs[3 * u];
-#pragma unroll
-                    for (int t = 6; t >= 1; t--) {  // l_{i+t,i} = row (i+t), slot 6-t ; descending j = i+t
-                        const double coef = (u + t < 6) ? cur[(u + t) * BW + 6 - t] : nxt[(u + t - 6) * BW + 6 - t];
-                        acc -= coef * w[(u + t) % 6];
-                    }
-                    w[u] = acc;
-                    bs[3 * u] = acc;
-                }
+                double* bs = Bs + 18 * (size_t)p + lane;
+                double pre5 = PRE2(5);
+                double pre4 = PRE2(4);
+                const double l5 = FIN2(5, pre5);
+                w[5] = l5;
+                double pre3 = PRE2(3);
+                const double l4 = FIN2(4, pre4);
+                w[4] = l4;
+                double pre2 = PRE2(2);
+                const double l3 = FIN2(3, pre3);
+                w[3] = l3;
+                double pre1 = PRE2(1);
+                const double l2 = FIN2(2, pre2);
+                w[2] = l2;
+                double pre0 = PRE2(0);
+                const double l1 = FIN2(1, pre1);
+                w[1] = l1;
+                const double l0 = FIN2(0, pre0);
+                w[0] = l0;
+                bs[0] = l0, bs[3] = l1, bs[6] = l2, bs[9] = l3, bs[12] = l4, bs[15] = l5;
             }
             __syncthreads();
         }
     }
+#undef LCOEF
+#undef PRE2
+#undef FIN2
     // ---- addPropCtoT (CPU.hpp:104-151), addPropCtoP (:154-161), rho (:989) ----
-    const double* cg_ = bv.c + 18 * (size_t)p0;
     for (int i = tid; i < M; i += 64) {
-        const double T1 = bv.T[p0 + i], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2;
-        const double* c = cg_ + 18 * i;
+        if (i != tid) {  // pieces beyond the first 64: not prefetched
+#pragma unroll
+            for (int q = 0; q < 18; q++) pc[q] = cg_[18 * i + q];
+            pT = bv.T[p0 + i];
+            pgdT = bv.gdT[p0 + i];
+        }
+        const double T1 = pT, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2;
         double s = 0.0;
         const int rows = (i < M - 1) ? 6 : 3;
         const int base = (i < M - 1) ? (6 * i + 3) : (6 * M - 3);
+#pragma unroll
         for (int d = 0; d < 3; d++) {
-            const double c1 = c[3 + d], c2 = c[6 + d], c3 = c[9 + d], c4 = c[12 + d], c5 = c[15 + d];
+            const double c1 = pc[3 + d], c2 = pc[6 + d], c3 = pc[9 + d], c4 = pc[12 + d], c5 = pc[15 + d];
             const double nVel = -(c1 + 2.0 * T1 * c2 + 3.0 * T2 * c3 + 4.0 * T3 * c4 + 5.0 * T4 * c5);
             const double nAcc = -(2.0 * c2 + 6.0 * T1 * c3 + 12.0 * T2 * c4 + 20.0 * T3 * c5);
             const double nJer = -(6.0 * c3 + 24.0 * T1 * c4 + 60.0 * T2 * c5);
@@ -687,13 +767,15 @@ __global__ void __launch_bounds__(64)
                 const double nSnp = -(24.0 * c4 + 120.0 * T1 * c5);
                 const double nCrk = -120.0 * c5;
                 const double B1[6] = {nSnp, nCrk, nVel, nVel, nAcc, nJer};
+#pragma unroll
                 for (int r = 0; r < 6; r++) s += B1[r] * Bs[3 * (base + r) + d];
             } else {
                 const double B2[3] = {nVel, nAcc, nJer};
+#pragma unroll
                 for (int r = 0; r < 3; r++) s += B2[r] * Bs[3 * (base + r) + d];
             }
         }
-        gT[i] = bv.gdT[p0 + i] + s + par.rho;
+        gT[i] = pgdT + s + par.rho;
         if (i < M - 1)
             for (int d = 0; d < 3; d++) gq[3 * i + d] = Bs[3 * (6 * i + 5) + d];
     }
@@ -702,7 +784,7 @@ __global__ void __launch_bounds__(64)
     if (tid == 0) {
         int offset = 0;
         for (int i = 0; i < coarseN; i++) {
-            const int iv = bv.intervals[co0 + i];
+            const int iv = ivs[i];
             double s = 0.0;
             for (int a = 0; a < iv; a++) s += gT[offset + a];
             gTc[i] = s / iv;
@@ -768,35 +850,23 @@ __global__ void __launch_bounds__(64)
         const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
         double* gxi = grad + dimT + bv.wp_xi_off[p0 + i];
         double qn = 0.0;
+#pragma unroll 8
         for (int a = 0; a < k; a++) qn += xi[a] * xi[a];
         const double q1 = qn + 1.0, q1s = q1 * q1;
         const double gx = gq[3 * i], gy = gq[3 * i + 1], gz = gq[3 * i + 2];
         double gdot = 0.0;
+#pragma unroll 4
         for (int a = 0; a < k; a++) {
             const double r = 2.0 / q1 * xi[a];
             const double gd = (V[3 * (a + 1)] * gx + V[3 * (a + 1) + 1] * gy + V[3 * (a + 1) + 2] * gz) * r * 2.0;
             gdot += gd * xi[a];
         }
+#pragma unroll 4
         for (int a = 0; a < k; a++) {
             const double r = 2.0 / q1 * xi[a];
             const double gd = (V[3 * (a + 1)] * gx + V[3 * (a + 1) + 1] * gy + V[3 * (a + 1) + 2] * gz) * r * 2.0;
             gxi[a] = gd * 2.0 / q1 - xi[a] * 4.0 * gdot / q1s;
         }
-    }
-    // ---- cost = jerk energy + penalty + rho * sum(T) (CPU.hpp:542,406,988), sequential sums ----
-    if (tid == 63) {
-        double e = 0.0, pn = 0.0;
-        for (int i = 0; i < M; i++) e += bv.energy[p0 + i];
-        for (int i = 0; i < M; i++) pn += bv.pen[p0 + i];
-        double cost = e + pn;
-        double sT = 0.0;
-        if (par.softT) {
-            for (int i = 0; i < coarseN; i++) sT += par.c2 ? c2_forward(x[i]) : exp(x[i]);
-        } else {
-            // coarse T of the fixed-total-time map: recover from the fine T (sum over pieces of a polytope)
-            for (int i = 0; i < M; i++) sT += bv.T[p0 + i];
-        }
-        cost_out[b] = cost + par.rho * sT;
     }
 }
 
@@ -807,7 +877,9 @@ size_t forward_smem_bytes(int M, int coarseN) {
     const size_t ust = (size_t)6 * M * UST, tc = (size_t)coarseN + 1;
     return sizeof(double) * ((size_t)RING * BW + 32 + (ust > tc ? ust : tc));
 }
-size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1); }
+size_t backward_smem_bytes(int M, int coarseN) {
+    return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + (coarseN + 2) / 2 + 1);
+}
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
     PenaltyLaunch pl;

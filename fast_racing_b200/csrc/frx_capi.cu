@@ -359,7 +359,7 @@ int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double
     if (!b || !x_host || !cost_host || !grad_host) return FRX_ERR_INVALID_ARG;
     CK(cudaSetDevice(b->device));
     const size_t nx = sizeof(double) * (size_t)b->bv.total_x;
-    std::memcpy(b->x_pin, x_host, nx);
+    if (x_host != b->x_pin) std::memcpy(b->x_pin, x_host, nx);  // staging only for foreign (pageable) buffers
     CK(cudaEventRecord(b->ev0, b->stream));
     CK(cudaMemcpyAsync(b->x_dev, b->x_pin, nx, cudaMemcpyHostToDevice, b->stream));
     CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, b->x_dev, b->cost_dev, b->g_dev, b->stream));
@@ -370,8 +370,16 @@ int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
     b->last_ms = ms;
-    std::memcpy(grad_host, b->g_pin, nx);
-    std::memcpy(cost_host, b->cost_pin, sizeof(double) * b->bv.B);
+    if (grad_host != b->g_pin) std::memcpy(grad_host, b->g_pin, nx);
+    if (cost_host != b->cost_pin) std::memcpy(cost_host, b->cost_pin, sizeof(double) * b->bv.B);
+    return FRX_OK;
+}
+
+int frx_batch_host_buffers(frx_batch* b, double** x_pinned, double** cost_pinned, double** grad_pinned) {
+    if (!b) return FRX_ERR_INVALID_ARG;
+    if (x_pinned) *x_pinned = b->x_pin;
+    if (cost_pinned) *cost_pinned = b->cost_pin;
+    if (grad_pinned) *grad_pinned = b->g_pin;
     return FRX_OK;
 }
 

@@ -101,6 +101,9 @@ int frx_batch_initial_guess(frx_batch *b, double *x_host);
  * trajectory of the batch.  Host buffers: x (packed), cost[count], grad (packed).  Copies
  * host->device, runs the kernels, copies back, synchronises. */
 int frx_batch_eval(frx_batch *b, const double *x_host, double *cost_host, double *grad_host);
+/* The batch's own pinned (page-locked) host buffers: x[total], cost[count], grad[total].  Passing exactly these
+ * pointers to frx_batch_eval skips the staging copies (the host<->device transfers then run directly from/to them). */
+int frx_batch_host_buffers(frx_batch *b, double **x_pinned, double **cost_pinned, double **grad_pinned);
 /* Same with device-resident buffers on the given CUDA stream (cudaStream_t passed as void*;
  * NULL = the CUDA default stream, as everywhere in CUDA).  Asynchronous: no synchronisation. */
 int frx_batch_eval_device(frx_batch *b, const double *x_dev, double *cost_dev, double *grad_dev, void *stream);

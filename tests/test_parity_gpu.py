@@ -313,6 +313,16 @@ def test_c4_gradient_is_the_derivative_of_the_cost(c4_batch):
     assert np.median(err) < 1e-7 and err.max() < 1e-4
 
 
+def test_pinned_host_buffer_api_matches_staged_api(c4_batch):
+    batch, _ = c4_batch
+    x = batch.initial_guess() + 0.1 * np.random.default_rng(3).normal(size=batch.total_x)
+    c_h, g_h = batch.eval(x)
+    xp, cp, gp = batch.host_buffers()
+    xp[:] = x
+    batch.eval_pinned()
+    assert np.array_equal(cp, c_h) and np.array_equal(gp, g_h)
+
+
 def test_device_pointer_api_matches_host_api(c4_batch):
     import torch
 
