@@ -124,7 +124,7 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
 // smem: ring[RING][16] | scratch[32] | ust[N][9] (aliased by Tc[coarseN] during the prologue)
 __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
-    const int b = blockIdx.x;
+    const int b = bv.sub_traj0 + blockIdx.x;
     if (bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -291,14 +291,14 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 // Same mathematics as the reference, different association (inside the stated tolerance).
 //
 // smem: cf[ppc][60] derivative coefficient tables | fc[ppc][6*max_faces] | part[20][threads]
-#define PEN_THREADS 128
+#define PEN_THREADS 64
 #define CF 60  // per piece: 18 pos + 15 vel + 12 acc + 9 jerk + 6 snap coefficients
 
-__global__ void __launch_bounds__(PEN_THREADS, 4) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
+__global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
-    const int gp_base = blockIdx.x * pl.ppc;
-    const int npieces = min(pl.ppc, bv.total_pieces - gp_base);
+    const int gp_base = bv.sub_piece0 + blockIdx.x * pl.ppc;
+    const int npieces = min(pl.ppc, bv.sub_piece1 - gp_base);
     double* cf = sm;
     double* fc = cf + (size_t)pl.ppc * CF;
     double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
     extern __shared__ double sm[];
-    const int b = blockIdx.x;
+    const int b = bv.sub_traj0 + blockIdx.x;
     if (bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -893,7 +893,7 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
     }
     pl.spt = best_spt;
     pl.tpp = (S + pl.spt - 1) / pl.spt;
-    pl.threads = 128;
+    pl.threads = 64;
     pl.ppc = pl.threads / pl.tpp;
     if (pl.ppc < 1) pl.ppc = 1;
     pl.grid = (bv.total_pieces + pl.ppc - 1) / pl.ppc;
@@ -911,30 +911,67 @@ cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem)
     return e;
 }
 
-cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
-                        const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
-    minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bv, x_dev);
-    penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
-    minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+// One batched evaluation.  The banded kernels K1/K3 are latency-bound (a dependent chain per trajectory) and the
+// penalty kernel K2 is throughput-bound, so the batch is cut into sub-batches that are software-pipelined over two
+// streams: K1 of sub-batch i+1 runs under K2 of sub-batch i, K3 of sub-batch i under K2 of sub-batch i+1.
+// `piece_off_host` = host copy of bv.piece_off.  aux/ev*: helper stream and events owned by the batch.
+cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                                  const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, cudaStream_t aux,
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,
+                                  int nsub) {
+    const int B = bv0.B;
+    if (nsub < 2 || B < 2 * nsub || !aux) {
+        BatchView bv = bv0;
+        bv.sub_traj0 = 0, bv.sub_piece0 = 0, bv.sub_piece1 = bv.total_pieces;
+        minco_forward_kernel<<<B, 64, fwd_smem, st>>>(bv, x_dev);
+        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
+        minco_backward_kernel<<<B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+        return cudaGetLastError();
+    }
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(aux, ev_fork, 0);
+    for (int i = 0; i < nsub; i++) {
+        const int t0 = (int)((long long)B * i / nsub), t1 = (int)((long long)B * (i + 1) / nsub);
+        BatchView bv = bv0;
+        bv.sub_traj0 = t0;
+        bv.sub_piece0 = piece_off_host[t0];
+        bv.sub_piece1 = piece_off_host[t1];
+        cudaStream_t s = (i & 1) ? aux : st;
+        if (i == 1) cudaStreamWaitEvent(aux, ev_k1, 0);  // stagger: the second stream starts one K1 later
+        minco_forward_kernel<<<t1 - t0, 64, fwd_smem, s>>>(bv, x_dev);
+        if (i == 0) cudaEventRecord(ev_k1, st);
+        const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
+        penalty_kernel<<<grid, pl.threads, pl.smem, s>>>(bv, pl);
+        minco_backward_kernel<<<t1 - t0, 64, bwd_smem, s>>>(bv, x_dev, cost_dev, grad_dev);
+    }
+    cudaEventRecord(ev_join, aux);
+    cudaStreamWaitEvent(st, ev_join, 0);
     return cudaGetLastError();
 }
 
+cudaError_t launch_eval(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                        const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
+    return launch_eval_pipelined(bv0, pl, fwd_smem, bwd_smem, x_dev, cost_dev, grad_dev, st, nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, 1);
+}
 
 // Per-kernel device times of `reps` evaluations: CUDA events on the launching stream around each
 // of the three kernels.  ms[3] = average duration of K1, K2, K3.
 cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                          const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms) {
+    BatchView bvw = bv;
+    bvw.sub_traj0 = 0, bvw.sub_piece0 = 0, bvw.sub_piece1 = bv.total_pieces;
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
     ms[0] = ms[1] = ms[2] = 0.0;
     cudaError_t err = cudaSuccess;
     for (int r = 0; r < reps && err == cudaSuccess; r++) {
         cudaEventRecord(ev[0], st);
-        minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bv, x_dev);
+        minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bvw, x_dev);
         cudaEventRecord(ev[1], st);
-        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
+        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bvw, pl);
         cudaEventRecord(ev[2], st);
-        minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+        minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bvw, x_dev, cost_dev, grad_dev);
         cudaEventRecord(ev[3], st);
         err = cudaStreamSynchronize(st);
         for (int k = 0; k < 3 && err == cudaSuccess; k++) {

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -21,6 +22,10 @@ PenaltyLaunch plan_penalty(const BatchView& bv);
 cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);
 cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st);
+cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
+                                  const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, cudaStream_t aux,
+                                  cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,
+                                  int nsub);
 cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                          const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);
 double measure_fp64_tflops();
@@ -49,8 +54,13 @@ struct frx_batch {
     BatchView bv{};
     PenaltyLaunch pl{};
     size_t fwd_smem = 0, bwd_smem = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_k1 = nullptr, ev_join = nullptr;
+    int nsub = 1;  // sub-batches of the pipelined evaluation (FRX_EVAL_SUBBATCHES); measured on B200: K2 fills the register
+                   // file (8 CTAs x 64 thr x 128 regs), so K1/K3 cannot co-reside and pipelining only adds tails -> default off
+    cudaError_t eval_on(const double* x, double* cost, double* grad, cudaStream_t st) {
+        return launch_eval_pipelined(bv, pl, fwd_smem, bwd_smem, x, cost, grad, st, aux, ev_fork, ev_k1, ev_join, piece_off.data(), nsub);
+    }
     double last_ms = 0.0;
     std::vector<DevBuf> bufs;
     // persistent device-side x / cost / grad for the host-buffer API
@@ -119,6 +129,10 @@ void frx_batch_destroy(frx_batch* b) {
     if (b->cost_pin) cudaFreeHost(b->cost_pin);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_k1) cudaEventDestroy(b->ev_k1);
+    if (b->ev_join) cudaEventDestroy(b->ev_join);
+    if (b->aux) cudaStreamDestroy(b->aux);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -278,6 +292,11 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "stream");
     if ((e = cudaEventCreate(&b->ev0)) != cudaSuccess) return fail(e, "event");
     if ((e = cudaEventCreate(&b->ev1)) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "aux stream");
+    if ((e = cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&b->ev_k1, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
+    if (const char* ns = getenv("FRX_EVAL_SUBBATCHES")) b->nsub = std::max(1, atoi(ns));
     b->pl = plan_penalty(bv);
     if (b->pl.smem > 227 * 1024) {
         frx_batch_destroy(b);
@@ -344,14 +363,14 @@ int frx_batch_initial_guess(frx_batch* b, double* x_host) {
     return FRX_OK;
 }
 
-int frx_batch_eval_launches(const frx_batch* b) { return b ? 3 : FRX_ERR_INVALID_ARG; }
+int frx_batch_eval_launches(const frx_batch* b) { return b ? 3 * ((b->nsub >= 2 && b->bv.B >= 2 * b->nsub) ? b->nsub : 1) : FRX_ERR_INVALID_ARG; }
 void* frx_batch_stream(frx_batch* b) { return b ? (void*)b->stream : nullptr; }
 
 int frx_batch_eval_device(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream) {
     if (!b || !x_dev || !cost_dev || !grad_dev) return FRX_ERR_INVALID_ARG;
     CK(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, st));
+    CK(b->eval_on(x_dev, cost_dev, grad_dev, st));
     return FRX_OK;
 }
 
@@ -362,7 +381,7 @@ int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double
     if (x_host != b->x_pin) std::memcpy(b->x_pin, x_host, nx);  // staging only for foreign (pageable) buffers
     CK(cudaEventRecord(b->ev0, b->stream));
     CK(cudaMemcpyAsync(b->x_dev, b->x_pin, nx, cudaMemcpyHostToDevice, b->stream));
-    CK(launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, b->x_dev, b->cost_dev, b->g_dev, b->stream));
+    CK(b->eval_on(b->x_dev, b->cost_dev, b->g_dev, b->stream));
     CK(cudaMemcpyAsync(b->g_pin, b->g_dev, nx, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->cost_pin, b->cost_dev, sizeof(double) * b->bv.B, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaEventRecord(b->ev1, b->stream));
@@ -496,7 +515,7 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     io.rel_tol = rel_tol;
     io.stream = b->stream;
     auto eval = [b](const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
-        return launch_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, st);
+        return b->eval_on(x_dev, cost_dev, grad_dev, st);
     };
     CK(cudaEventRecord(b->ev0, b->stream));
     s = solver_run(b->solver, b->bv, io, eval);

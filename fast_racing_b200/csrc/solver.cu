@@ -89,13 +89,27 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
         const double* sl = S + (size_t)l * n;
         const double* yl = Y + (size_t)l * n;
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-        for (int i = lane; i < n; i += 32) {
-            const double s = sl[i], y = yl[i], yni = yn[i], sni = sn[i], gi = g[i];
-            a0 += s * yni;
-            a1 += y * yni;
-            a2 += y * sni;
-            a3 += s * gi;
-            a4 += y * gi;
+        // 8 elements per lane per trip, all loads issued before use (HBM-latency bound otherwise)
+        for (int i0 = lane; i0 < n; i0 += 256) {
+            double s[8], y[8], yni[8], sni[8], gi[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int i = i0 + 32 * e;
+                const bool in = i < n;
+                s[e] = in ? sl[i] : 0.0;
+                y[e] = in ? yl[i] : 0.0;
+                yni[e] = in ? yn[i] : 0.0;
+                sni[e] = in ? sn[i] : 0.0;
+                gi[e] = in ? g[i] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                a0 += s[e] * yni[e];
+                a1 += y[e] * yni[e];
+                a2 += y[e] * sni[e];
+                a3 += s[e] * gi[e];
+                a4 += y[e] * gi[e];
+            }
         }
         a0 = warp_sum(a0), a1 = warp_sum(a1), a2 = warp_sum(a2), a3 = warp_sum(a3), a4 = warp_sum(a4);
         if (lane == 0) {
@@ -113,66 +127,101 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
     }
     __syncthreads();
     // ---- loop 1 (newest -> oldest): alpha_j = (s_j . q) / ys_j,  q -= alpha_j y_j ----
-    if (warp == 0) {
-        double bq[4] = {0, 0, 0, 0};
-        int j = end;
-        double row[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) row[q] = (lane + 32 * q < m) ? SY[(size_t)j * m + lane + 32 * q] : 0.0;
-        for (int it = 0; it < bound; it++) {
-            const int jn = (j + m - 1) % m;
-            double nxt[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) nxt[q] = (lane + 32 * q < m) ? SY[(size_t)jn * m + lane + 32 * q] : 0.0;
-            double v = bq[0] * row[0] + bq[1] * row[1] + bq[2] * row[2] + bq[3] * row[3];
-            v = warp_sum(v);
-            const double alpha = (v - sg[j]) / ysv[j];
-            if (lane == 0) al[j] = alpha;
-            if ((j & 31) == lane) bq[j >> 5] = -alpha;
-#pragma unroll
-            for (int q = 0; q < 4; q++) row[q] = nxt[q];
-            j = jn;
-        }
-        const double gamma = ysv[end] / YY[(size_t)end * m + end];  // ys / yy of the newest pair
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (lane + 32 * q < 128) cb[lane + 32 * q] = bq[q] * gamma;
-        if (lane == 0) sh_gamma = gamma;
-    }
+    // Blocked by 16 history pairs: the contribution of all EARLIER blocks to the 16 rows of a block is a dense
+    // 16 x (#earlier) mat-vec done by the whole CTA (16 threads per row, coalesced row reads, one global round
+    // trip per block); only the 16 x 16 diagonal block is sequential, from shared memory, on 16 lanes.
+    // Age order: o = 0 is the newest pair, slot(o) = (end - o) mod m.
+    __shared__ double tpart[16];
+    __shared__ double dblk[16][17];
+    const int rr = tid >> 4, cc = tid & 15;  // 16 rows x 16 threads
+    for (int l = tid; l < 128; l += UPD_THREADS) cb[l] = 0.0, ca[l] = 0.0;
     __syncthreads();
-    const double dg = -sh_gamma;  // coefficient of g
+    for (int ob = 0; ob < bound; ob += 16) {
+        const int nb = min(16, bound - ob);
+        {
+            double t = 0.0;
+            if (rr < nb) {
+                const int j = (end - (ob + rr) + 2 * m) % m;
+                const double* row = SY + (size_t)j * m;
+                for (int o2 = cc; o2 < ob; o2 += 16) {
+                    const int l = (end - o2 + 2 * m) % m;
+                    t += cb[l] * row[l];
+                }
+                if (cc < nb) dblk[rr][cc] = row[(end - (ob + cc) + 2 * m) % m];
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 16);
+            if (cc == 0) tpart[rr] = t;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double bl = 0.0;  // lane c < 16 holds the coefficient of pair ob + c once computed
+            for (int r2 = 0; r2 < nb; r2++) {
+                const int j = (end - (ob + r2) + 2 * m) % m;
+                double v = (lane < r2) ? bl * dblk[r2][lane] : 0.0;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+                const double alpha = (v + tpart[r2] - sg[j]) / ysv[j];
+                if (lane == r2) {
+                    bl = -alpha;
+                    al[j] = alpha;
+                    cb[j] = -alpha;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) sh_gamma = ysv[end] / YY[(size_t)end * m + end];  // ys / yy of the newest pair
+    __syncthreads();
+    const double gamma = sh_gamma;
+    for (int l = tid; l < 128; l += UPD_THREADS) cb[l] *= gamma;
+    __syncthreads();
+    const double dg = -gamma;  // coefficient of g
     // t_j = dg * (y_j . g) + sum_l b_l (y_j . y_l): independent of the second recursion
     if (tid < bound) {
         double t = 0.0;
+#pragma unroll 4
         for (int l = 0; l < bound; l++) t += cb[l] * YY[(size_t)l * m + tid];
         tv[tid] = dg * yg[tid] + t;
     }
     __syncthreads();
     // ---- loop 2 (oldest -> newest): beta = (y_j . r) / ys_j,  r += (alpha_j - beta) s_j ----
-    if (warp == 0) {
-        double aq[4] = {0, 0, 0, 0};
-        int j = (end + m - (bound - 1)) % m;
-        double row[4];
+    // Same blocking; age order now o = 0 is the OLDEST pair: slot(o) = (end - (bound-1) + o) mod m; the row of
+    // pair j is SYT[j][l] = s_l . y_j.
+    for (int ob = 0; ob < bound; ob += 16) {
+        const int nb = min(16, bound - ob);
+        {
+            double t = 0.0;
+            if (rr < nb) {
+                const int j = (end - (bound - 1) + (ob + rr) + 2 * m) % m;
+                const double* row = SYT + (size_t)j * m;
+                for (int o2 = cc; o2 < ob; o2 += 16) {
+                    const int l = (end - (bound - 1) + o2 + 2 * m) % m;
+                    t += ca[l] * row[l];
+                }
+                if (cc < nb) dblk[rr][cc] = row[(end - (bound - 1) + (ob + cc) + 2 * m) % m];
+            }
 #pragma unroll
-        for (int q = 0; q < 4; q++) row[q] = (lane + 32 * q < m) ? SYT[(size_t)j * m + lane + 32 * q] : 0.0;
-        for (int it = 0; it < bound; it++) {
-            const int jn = (j + 1) % m;
-            double nxt[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) nxt[q] = (lane + 32 * q < m) ? SYT[(size_t)jn * m + lane + 32 * q] : 0.0;
-            double v = aq[0] * row[0] + aq[1] * row[1] + aq[2] * row[2] + aq[3] * row[3];
-            v = warp_sum(v);
-            const double beta = (tv[j] + v) / ysv[j];
-            if ((j & 31) == lane) aq[j >> 5] = al[j] - beta;
-#pragma unroll
-            for (int q = 0; q < 4; q++) row[q] = nxt[q];
-            j = jn;
+            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 16);
+            if (cc == 0) tpart[rr] = t;
         }
+        __syncthreads();
+        if (warp == 0) {
+            double al2 = 0.0;
+            for (int r2 = 0; r2 < nb; r2++) {
+                const int j = (end - (bound - 1) + (ob + r2) + 2 * m) % m;
+                double v = (lane < r2) ? al2 * dblk[r2][lane] : 0.0;
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (lane + 32 * q < 128) ca[lane + 32 * q] = aq[q];
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+                const double beta = (tv[j] + tpart[r2] + v) / ysv[j];
+                if (lane == r2) {
+                    al2 = al[j] - beta;
+                    ca[j] = al2;
+                }
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- pass 2: d = dg*g + sum_l ca_l s_l + cb_l y_l ----
     for (int base = 0; base < n; base += UPD_THREADS * 4) {
         double acc[4];
@@ -182,6 +231,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
             idx[e] = base + e * UPD_THREADS + tid;
             acc[e] = idx[e] < n ? dg * g[idx[e]] : 0.0;
         }
+#pragma unroll 8
         for (int l = 0; l < bound; l++) {
             const double a = ca[l], bb = cb[l];
             const double* sl = S + (size_t)l * n;
