@@ -206,14 +206,16 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # clocks are sampled (nvidia-smi, ~10 Hz) from here to the end of the end-to-end leg: warm-up, the timed region, the
+    # per-kernel pass and the host-buffer pass all run the same three kernels back to back
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # ---- warm-up ----
     for _ in range(max(a.warmup, 3)):
         batch.eval_device(xd.data_ptr(), cd.data_ptr(), gd.data_ptr(), sp)
     sync_all()
 
     # ---- timed region: K steps, L2 flushed between steps (outside the event pairs) ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     sync_all()
     for k in range(a.steps):
@@ -230,7 +232,6 @@ def main():
         flush.fill_(float(k))
         kms += batch.profile_eval(xd.data_ptr(), cd.data_ptr(), gd.data_ptr(), sp, 1) / a.steps
     torch.cuda.synchronize()
-    clocks = sampler.summary()
 
     # ---- end-to-end through the public host-buffer API (H2D of x, D2H of cost + grad every step) ----
     # The caller keeps x / reads (cost, grad) in the batch's pinned host buffers (frx_batch_host_buffers), so each step is
@@ -247,6 +248,16 @@ def main():
         sink = float(cost_h[0]) + float(grad_h[-1])  # the step's result is read on the host
     e2e_s = time.perf_counter() - t0
     assert np.isfinite(cost_h).all() and np.isfinite(grad_h).all()
+    # the timed regions are only milliseconds long: keep the same kernels running until the sampler has seen the GPU
+    # under this load for >= 1.5 s (not part of any reported time)
+    t_busy = time.perf_counter()
+    while time.perf_counter() - t_busy < 1.5 or len(sampler.rows) < 8:
+        for _ in range(50):
+            batch.eval_device(xd.data_ptr(), cd.data_ptr(), gd.data_ptr(), sp)
+        torch.cuda.synchronize()
+        if time.perf_counter() - t_busy > 6.0:
+            break
+    clocks = sampler.summary()
 
     # max over ranks
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)

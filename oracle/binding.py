@@ -179,3 +179,89 @@ def ref_lbfgs():
     R.ref_lbfgs_optimize.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), EVAL_T, C.c_void_p, C.c_int,
                                      C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
     return R
+
+
+class RefGcopter:
+    """The reference's own SE3GCOPTER (verbatim se3gcopter_cpu.hpp + trajectory.hpp + lbfgs.hpp compiled over the
+    Eigen-API shim, oracle/_ref/libfrx_ref.so).  `problem` must carry V-polytopes.  Available only where oracle/_ref was
+    built (a box that has /root/reference) or travelled with the snapshot."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(REF_GCOPTER)
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            R = C.CDLL(REF_GCOPTER)
+            P, vp, ci, cd = C.POINTER, C.c_void_p, C.c_int, C.c_double
+            R.ref_create.restype = vp
+            R.ref_create.argtypes = [vp]
+            R.ref_destroy.argtypes = [vp]
+            R.ref_dims.argtypes = [vp, P(ci), P(ci), P(ci), P(ci)]
+            R.ref_tables.argtypes = [vp, P(ci), P(ci), P(ci), P(ci)]
+            R.ref_eval.restype = cd
+            R.ref_eval.argtypes = [vp, P(cd), P(cd), ci]
+            R.ref_initial_guess.argtypes = [vp, P(cd)]
+            R.ref_forward.argtypes = [vp, P(cd), P(cd), P(cd)]
+            R.ref_optimize.restype = cd
+            R.ref_optimize.argtypes = [vp, cd, P(cd), P(cd)]
+            cls._lib = R
+        return cls._lib
+
+    def __init__(self, problem):
+        self.R = self.lib()
+        assert problem.vert_off is not None
+        self.problem = problem
+        self._s = problem.as_struct()
+        self.h = self.R.ref_create(C.cast(C.pointer(self._s), C.c_void_p))
+        if not self.h:
+            raise RuntimeError("reference SE3GCOPTER::setup returned false")
+        n, M, dt, dpp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.R.ref_dims(self.h, C.byref(n), C.byref(M), C.byref(dt), C.byref(dpp))
+        self.n, self.pieces, self.dim_t, self.dim_p = n.value, M.value, dt.value, dpp.value
+
+    def close(self):
+        if self.h:
+            self.R.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tables(self):
+        intervals = np.zeros(self.problem.n_poly, np.int32)
+        idx_hs = np.zeros(self.pieces, np.int32)
+        idx_vs = np.zeros(max(self.pieces - 1, 1), np.int32)
+        cons = np.zeros(self.pieces, np.int32)
+        self.R.ref_tables(self.h, _ip(intervals), _ip(idx_hs), _ip(idx_vs), _ip(cons))
+        return dict(intervals=intervals, idx_hs=idx_hs, idx_vs=idx_vs[: self.pieces - 1], cons=cons)
+
+    def initial_guess(self):
+        x = np.zeros(self.n)
+        self.R.ref_initial_guess(self.h, _dp(x))
+        return x
+
+    def eval(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        g = np.zeros(self.n)
+        f = self.R.ref_eval(self.h, _dp(x), _dp(g), self.n)
+        return f, g
+
+    def forward(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        T = np.zeros(self.pieces)
+        c = np.zeros(18 * self.pieces)
+        self.R.ref_forward(self.h, _dp(x), _dp(T), _dp(c))
+        return T, c
+
+    def optimize(self, rel_tol):
+        dur = np.zeros(self.pieces)
+        co = np.zeros(18 * self.pieces)
+        j = self.R.ref_optimize(self.h, rel_tol, _dp(dur), _dp(co))
+        return dict(jerk_cost=j, durations=dur, coeffs=co)

@@ -9,11 +9,11 @@
 // P,V,T-,T+,B).  Small fixed-size reductions (3-vector dots, 3x3 products) are summed left to
 // right; real Eigen may associate them differently (last-bit effects only).
 //
-// Parity status: the reference cannot be built here with its real dependency (Eigen is not in
-// the image and is not vendored).  This restatement is pinned (a) by its own finite-difference
-// and analytic known-answer tests and (b) against the verbatim reference headers compiled over
-// the Eigen-API shim in oracle/eigen_shim (oracle/_ref/libfrx_ref.so) when /root/reference exists;
-// see oracle/README.md and DESIGN.md for what that does and does not prove.
+// Parity status: PINNED against the reference's own code.  The reference build needs Eigen (not in the image, not
+// vendored), so the verbatim se3gcopter_cpu.hpp + trajectory.hpp + lbfgs.hpp are compiled over our Eigen-API shim
+// (oracle/eigen_shim, oracle/ref_gcopter_wrap.cpp -> oracle/_ref/libfrx_ref.so) and this restatement is BIT-IDENTICAL to
+// that build on tables, start point, cost, gradient, coefficients and the complete optimize() result
+// (tests/test_oracle_cpu.py); plus finite-difference and analytic known-answer tests.  See oracle/README.md, DESIGN.md §6.
 #pragma once
 #include <algorithm>
 #include <cfloat>

@@ -5,8 +5,9 @@ Each fixture holds one small problem (faces, V-polytopes, parameters), evaluatio
   * the CPU oracle (oracle/gcopter_oracle.hpp): cost, gradient, T, q, c, index tables, initial guess,
   * the oracle's objective driven by the VERBATIM reference lbfgs.hpp (oracle/_ref/libref_lbfgs.so):
     final x / cost / status — and the restated L-BFGS must reproduce them bit for bit,
-  * when oracle/_ref/libfrx_ref.so exists (verbatim se3gcopter_cpu.hpp over the Eigen-API shim): the
-    reference's own cost/gradient at the same points ("ref_cost", "ref_grad").
+  * the reference's OWN code — verbatim se3gcopter_cpu.hpp + trajectory.hpp + lbfgs.hpp compiled over the Eigen-API shim
+    (oracle/_ref/libfrx_ref.so): cost / gradient at the same points ("ref_cost", "ref_grad") and its complete optimize()
+    result ("ref_opt_*") — asserted BIT-IDENTICAL to the oracle's at generation time.
 """
 import ctypes as C
 import os
@@ -59,6 +60,18 @@ def main():
         out.update(opt_x=r["x"], opt_final_cost=r["final_cost"], opt_jerk_cost=r["jerk_cost"], opt_status=r["status"],
                    opt_iterations=r["iterations"], opt_evaluations=r["evaluations"], opt_durations=r["durations"],
                    opt_coeffs=r["coeffs"], opt_rel_tol=tol)
+        if ob.RefGcopter.available():
+            # the reference's OWN code (verbatim se3gcopter_cpu.hpp over the Eigen-API shim) on the same inputs
+            rg = ob.RefGcopter(pv)
+            rc, rgr = zip(*[rg.eval(x) for x in xs])
+            assert np.array_equal(np.array(rc), np.array(costs)) and np.array_equal(np.stack(rgr), np.stack(grads)), \
+                f"{name}: oracle deviates from the verbatim reference source"
+            assert np.array_equal(rg.initial_guess(), x0)
+            ro = rg.optimize(tol)
+            assert ro["jerk_cost"] == r["jerk_cost"] and np.array_equal(ro["durations"], r["durations"])
+            out.update(ref_cost=np.array(rc), ref_grad=np.stack(rgr), ref_opt_jerk_cost=ro["jerk_cost"], ref_opt_durations=ro["durations"],
+                       ref_opt_coeffs=ro["coeffs"])
+            rg.close()
         if R is not None:
             xr = x0.copy()
             fr = C.c_double()

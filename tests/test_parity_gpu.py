@@ -145,6 +145,9 @@ def test_cuda_matches_golden_vectors(name):
     assert np.array_equal(batch.initial_guess(), z["x0"])
     for i, x in enumerate(z["xs"]):
         cost, grad = batch.eval(x)
+        # ref_* = outputs of the reference's own code (verbatim se3gcopter_cpu.hpp over the Eigen-API shim)
+        assert abs(cost[0] - z["ref_cost"][i]) <= COST_RTOL * abs(z["ref_cost"][i])
+        assert rel_err(grad, z["ref_grad"][i]) <= GRAD_RTOL
         assert abs(cost[0] - z["cost"][i]) <= COST_RTOL * abs(z["cost"][i])
         assert rel_err(grad, z["grad"][i]) <= GRAD_RTOL
         dbg = batch.debug_fetch()
