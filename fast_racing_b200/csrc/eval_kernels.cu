@@ -949,6 +949,21 @@ cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl,
     return cudaGetLastError();
 }
 
+// The three kernels for the trajectory window [t0, t1) on one stream (used by the chunked host-buffer path, where the
+// host<->device copies of one chunk overlap the kernels of the other).
+cudaError_t launch_eval_window(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem, const double* x_dev,
+                               double* cost_dev, double* grad_dev, cudaStream_t st, int t0, int t1, const int* piece_off_host) {
+    BatchView bv = bv0;
+    bv.sub_traj0 = t0;
+    bv.sub_piece0 = piece_off_host[t0];
+    bv.sub_piece1 = piece_off_host[t1];
+    minco_forward_kernel<<<t1 - t0, 64, fwd_smem, st>>>(bv, x_dev);
+    const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
+    penalty_kernel<<<grid, pl.threads, pl.smem, st>>>(bv, pl);
+    minco_backward_kernel<<<t1 - t0, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_eval(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
     return launch_eval_pipelined(bv0, pl, fwd_smem, bwd_smem, x_dev, cost_dev, grad_dev, st, nullptr, nullptr, nullptr, nullptr,

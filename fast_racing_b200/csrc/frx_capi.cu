@@ -22,6 +22,8 @@ PenaltyLaunch plan_penalty(const BatchView& bv);
 cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);
 cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st);
+cudaError_t launch_eval_window(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem, const double* x_dev,
+                               double* cost_dev, double* grad_dev, cudaStream_t st, int t0, int t1, const int* piece_off_host);
 cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                                   const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, cudaStream_t aux,
                                   cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,
@@ -56,6 +58,7 @@ struct frx_batch {
     size_t fwd_smem = 0, bwd_smem = 0;
     cudaStream_t stream = nullptr, aux = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_k1 = nullptr, ev_join = nullptr;
+    int e2e_chunks = 2;  // chunks of the host-buffer path: copies of one chunk overlap the kernels of the other (FRX_E2E_CHUNKS)
     int nsub = 1;  // sub-batches of the pipelined evaluation (FRX_EVAL_SUBBATCHES); measured on B200: K2 fills the register
                    // file (8 CTAs x 64 thr x 128 regs), so K1/K3 cannot co-reside and pipelining only adds tails -> default off
     cudaError_t eval_on(const double* x, double* cost, double* grad, cudaStream_t st) {
@@ -297,6 +300,7 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     if ((e = cudaEventCreateWithFlags(&b->ev_k1, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
     if ((e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
     if (const char* ns = getenv("FRX_EVAL_SUBBATCHES")) b->nsub = std::max(1, atoi(ns));
+    if (const char* nc = getenv("FRX_E2E_CHUNKS")) b->e2e_chunks = std::max(1, atoi(nc));
     b->pl = plan_penalty(bv);
     if (b->pl.smem > 227 * 1024) {
         frx_batch_destroy(b);
@@ -380,10 +384,30 @@ int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double
     const size_t nx = sizeof(double) * (size_t)b->bv.total_x;
     if (x_host != b->x_pin) std::memcpy(b->x_pin, x_host, nx);  // staging only for foreign (pageable) buffers
     CK(cudaEventRecord(b->ev0, b->stream));
-    CK(cudaMemcpyAsync(b->x_dev, b->x_pin, nx, cudaMemcpyHostToDevice, b->stream));
-    CK(b->eval_on(b->x_dev, b->cost_dev, b->g_dev, b->stream));
-    CK(cudaMemcpyAsync(b->g_pin, b->g_dev, nx, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaMemcpyAsync(b->cost_pin, b->cost_dev, sizeof(double) * b->bv.B, cudaMemcpyDeviceToHost, b->stream));
+    const int B = b->bv.B;
+    const int nch = (B >= 64 && b->e2e_chunks > 1) ? std::min(b->e2e_chunks, B / 32) : 1;
+    if (nch <= 1) {
+        CK(cudaMemcpyAsync(b->x_dev, b->x_pin, nx, cudaMemcpyHostToDevice, b->stream));
+        CK(b->eval_on(b->x_dev, b->cost_dev, b->g_dev, b->stream));
+        CK(cudaMemcpyAsync(b->g_pin, b->g_dev, nx, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->cost_pin, b->cost_dev, sizeof(double) * B, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        // chunked: H2D(c) -> kernels(c) -> D2H(c) alternate between two streams, so that the PCIe copies of one chunk
+        // run under the kernels of the other
+        CK(cudaEventRecord(b->ev_fork, b->stream));
+        CK(cudaStreamWaitEvent(b->aux, b->ev_fork, 0));
+        for (int c = 0; c < nch; c++) {
+            const int t0 = (int)((long long)B * c / nch), t1 = (int)((long long)B * (c + 1) / nch);
+            const size_t o0 = (size_t)b->x_off[t0], o1 = (size_t)b->x_off[t1];
+            cudaStream_t s = (c & 1) ? b->aux : b->stream;
+            CK(cudaMemcpyAsync(b->x_dev + o0, b->x_pin + o0, sizeof(double) * (o1 - o0), cudaMemcpyHostToDevice, s));
+            CK(launch_eval_window(b->bv, b->pl, b->fwd_smem, b->bwd_smem, b->x_dev, b->cost_dev, b->g_dev, s, t0, t1, b->piece_off.data()));
+            CK(cudaMemcpyAsync(b->g_pin + o0, b->g_dev + o0, sizeof(double) * (o1 - o0), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(b->cost_pin + t0, b->cost_dev + t0, sizeof(double) * (t1 - t0), cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaEventRecord(b->ev_join, b->aux));
+        CK(cudaStreamWaitEvent(b->stream, b->ev_join, 0));
+    }
     CK(cudaEventRecord(b->ev1, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     float ms = 0.f;
