@@ -110,7 +110,8 @@ def cpu_baseline(problems_with_v, x_list, a, budget_s):
     reps1 = max(3, int(0.25 * budget_s / max(t1, 1e-6)))
     one = oracles[0].time_evals(x_list[0], reps1)
     one_core = reps1 / one
-    reps = max(2, int(0.75 * budget_s / max(t1, 1e-6) / max(1, (n_or + ncpu - 1) // ncpu)))
+    cal = ob.time_evals_mt(oracles, x_list[:n_or], 20, ncpu) / 20.0  # calibrated under load
+    reps = max(2, int(0.75 * budget_s / max(cal, 1e-6)))
     secs = ob.time_evals_mt(oracles, x_list[:n_or], reps, ncpu)
     allc = n_or * reps / secs
     for o in oracles:
@@ -142,9 +143,10 @@ def run_reference(a):
         x = o.initial_guess()
         xs.append(x + a.noise * rng.normal(size=x.size))
         oracles.append(o)
-    t1 = oracles[0].time_evals(xs[0], 2) / 2
-    per_step_budget = 120.0 / max(1, a.steps + a.warmup)
-    reps = max(1, int(per_step_budget / max(t1, 1e-6) / max(1, (n_or + ncpu - 1) // ncpu)))
+    # calibrate UNDER LOAD (all threads busy): per-evaluation time rises with SMT / memory contention
+    cal = ob.time_evals_mt(oracles, xs, 20, ncpu) / 20.0  # seconds for one evaluation of every trajectory on all threads
+    per_step_budget = 60.0 / max(1, a.steps + a.warmup)
+    reps = max(1, int(per_step_budget / max(cal, 1e-6)))
     for _ in range(a.warmup):
         ob.time_evals_mt(oracles, xs, reps, ncpu)
     t0 = time.perf_counter()
@@ -312,6 +314,14 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        traffic, traffic_src = None, None
+        try:  # dram__bytes_read+write of the penalty kernel per launch, from the committed `ncu --set full` capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")))
+            if (B, M, S, F) == (1024, 64, 33, 12):
+                traffic = tj["kernels"]["penalty_kernel"]["traffic_bytes"]
+                traffic_src = "profiles/r01b_dram_traffic.json (ncu --set full, same workload)"
+        except Exception:
+            pass
         pen_s = kms[1] * 1e-3
         achieved = ab["penalty_kernel"] * B / pen_s / 1e9
         fp64_peak = batch.lib.frx_measure_fp64_tflops()
@@ -332,7 +342,7 @@ def main():
             "gpu_launches": int(batch.eval_launches() * a.steps),
             "kernels_ms": {"minco_forward": kms[0], "penalty": kms[1], "minco_backward": kms[2]},
             "roofline": {"kernel": "penalty_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ab["penalty_kernel"] * B,
                          "note": "fp64-pipe-bound kernel: see roofline_fp64 (SURVEY.md §8d caveat)"},
             "roofline_fp64": {"kernel": "penalty_kernel", "bound": "fp64", "achieved": fl / pen_s / 1e12, "peak": fp64_peak,
