@@ -144,6 +144,7 @@ def load_library():
         "frx_batch_eval_launches": (ci, [vp]),
         "frx_batch_stream": (vp, [vp]),
         "frx_batch_host_buffers": (ci, [vp, P(P(cd)), P(P(cd)), P(P(cd))]),
+        "frx_batch_set_reference_order": (ci, [vp, ci]),
         "frx_eval": (cd, [vp, P(cd), P(cd), ci]),
         "frx_batch_optimize": (ci, [vp, cd, P(cd), P(cd), P(cd), P(cd), P(ci), P(ci), P(ci), P(cd)]),
         "frx_batch_argmin": (ci, [vp, P(ci), P(cd)]),
@@ -170,7 +171,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "frx_batch_create", "frx_batch_destroy", "frx_batch_count", "frx_batch_dims", "frx_batch_x_offsets",
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
-    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
+    "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_batch_set_reference_order", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version",
 ]
 
@@ -292,6 +293,10 @@ class Batch:
         grad = np.zeros(self.total_x)
         _check(self.lib.frx_batch_eval(self.h, _dp(x), _dp(cost), _dp(grad)), "frx_batch_eval")
         return cost, grad
+
+    def set_reference_order(self, on=True):
+        """Reference-order mode: bit-identical to the reference CPU code, slow (validation / reproducibility)."""
+        _check(self.lib.frx_batch_set_reference_order(self.h, 1 if on else 0), "set_reference_order")
 
     def host_buffers(self):
         """numpy views of the batch's pinned host buffers (x, cost, grad): eval_pinned() transfers straight from/to them."""

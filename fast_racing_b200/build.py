@@ -2,6 +2,10 @@
 
 Called by __graft_entry__.build(); the .so is git-ignored but travels to the GPU box with the
 snapshot.  No JIT, no torch extension machinery: the product is a plain C-ABI shared library.
+
+The device sources are compiled twice: the fast build (FMA contraction, reciprocal pivots, parallel
+reductions; namespace frx) and the reference-order build (-DFRX_EXACT --fmad=false; namespace
+frx_exact), which reproduces the reference's operation order bit for bit (DESIGN.md "Numerics").
 """
 import os
 import subprocess
@@ -9,33 +13,62 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libfrx.so")
-SOURCES = ["frx_capi.cu", "eval_kernels.cu", "solver.cu", "host_model.cpp", "host_geometry.cpp"]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-pthread", "-shared", "-x", "cu",
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-pthread", "-x", "cu"]
+# (source, object suffix, extra flags)
+UNITS = [
+    ("frx_capi.cu", "", []),
+    ("eval_kernels.cu", "", []),
+    ("solver.cu", "", []),
+    ("host_model.cpp", "", []),
+    ("host_geometry.cpp", "", []),
+    ("eval_kernels.cu", "_exact", ["-DFRX_EXACT=1", "--fmad=false"]),
+    ("solver.cu", "_exact", ["-DFRX_EXACT=1", "--fmad=false"]),
 ]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "frx.h"), __file__]
 
 
 def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "frx.h"), __file__]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ, exist_ok=True)
+    newest_hdr = max(os.path.getmtime(d) for d in _deps() if d.endswith((".cuh", ".hpp", ".h", ".py")))
+    procs, objs = [], []
+    for src, suffix, extra in UNITS:
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + suffix + ".o")
+        objs.append(obj)
+        srcp = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), newest_hdr):
+            continue
+        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
+        procs.append((src + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for name, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(f"---- {name} ----\n{out}")
+            failed = True
+        elif verbose:
+            sys.stderr.write(f"---- {name} ----\n{out}")
+    if failed:
+        raise RuntimeError("nvcc failed building libfrx.so")
+    r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libfrx.so")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc link failed")
     return OUT
 
 

@@ -31,6 +31,7 @@ struct BatchView {
     int max_samples;  // max cons+1
     // sub-batch window of this launch (the evaluation is pipelined over sub-batches on two streams)
     int sub_traj0;    // first trajectory handled by K1/K3 of this launch
+    int sub_traj1;    // one past the last trajectory of this launch
     int sub_piece0;   // first global piece handled by K2 of this launch
     int sub_piece1;   // one past the last global piece handled by K2 of this launch
     // per trajectory

@@ -14,10 +14,18 @@
 // roofline of each kernel.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cstdlib>
 
 #include "device_batch.cuh"
 
-namespace frx {
+#ifdef FRX_EXACT
+#define FRX_IMPL frx_exact  // reference-order build: -DFRX_EXACT --fmad=false (see build.py)
+#else
+#define FRX_IMPL frx_fast
+#endif
+
+namespace FRX_IMPL {
+using namespace frx;
 
 // ------------------------------------------------------------------------------------------------
 // Band storage used on the device: row-major, 16 doubles per row: slot (j - i + 6) for column j of
@@ -46,7 +54,11 @@ __device__ __forceinline__ double c2_forward(double t) {  // CPU.hpp:639-641
 // before) | [7..12] u_{i,i+1..i+6} | [13..15] right-hand side (x,y,z).  Rows are retired to bv.lu in the
 // same layout.
 #define RING 32
+#ifdef FRX_EXACT
+#define UST 10  // reference-order build: u_ii, u_{i,i+1..i+6}, y_{x,y,z} (division kept in the back substitution)
+#else
 #define UST 9  // compact store per row, pre-multiplied by 1/u_ii: u_{i,i+1..i+6}/u_ii, y_{x,y,z}/u_ii
+#endif
 
 // Entry tables of one junction block (rows 6i+3 .. 6i+8, CPU.hpp:446-476): value = coef * T^pow at
 // (row offset, band slot = column - row + 6).
@@ -117,7 +129,11 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
     for (int e = lane; e < cnt * UST; e += 32) {
         const int rr = e / UST, q = e - UST * rr;
         const double* rw = ring + ((row0 + rr) & (RING - 1)) * BW;
+#ifdef FRX_EXACT
+        ust[(size_t)(row0 + rr) * UST + q] = rw[6 + q];  // diagonal, upper band, y: unscaled
+#else
         ust[(size_t)(row0 + rr) * UST + q] = rw[7 + q] * rw[6];  // x_i = y_i/u_ii - sum_t (u_{i,i+t}/u_ii) x_{i+t}
+#endif
     }
 }
 
@@ -203,7 +219,9 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         fill_block(ring, bv, b, M, 1, lane, fl, loadT(1), loadq(1));
     }
     __syncthreads();
+#ifndef FRX_EXACT
     if (tid == 0) ring[6] = 1.0 / ring[6];
+#endif
     __syncthreads();
 
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
@@ -226,11 +244,19 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
                     double* pa = reinterpret_cast<double*>(rb + oi + cA);
                     double* pb = reinterpret_cast<double*>(rb + oi + cB);
                     double* pc = reinterpret_cast<double*>(rb + oi + cC);
+#ifdef FRX_EXACT
+                    const double l = *pa / rk[6];  // a_ik / u_kk as the reference (trajectory.hpp:667)
+#else
                     const double l = *pa * rk[6];  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
+#endif
                     const double v0 = pb[0] - l * rk2[7];
                     const double v1 = pb[3] - l * rk2[10];
                     const double v2 = *pc - l * rk2[13];
+#ifdef FRX_EXACT
+                    pb[0] = v0;
+#else
                     pb[0] = (lane == 0) ? fast_rcp(v0) : v0;  // lane 0 (r = 0, cg = 0) owns the next pivot: store 1/u
+#endif
                     pb[3] = v1;
                     *pc = v2;
                     *pend = l_pend;  // multiplier of the PREVIOUS step (nobody reads column k-1 any more)
@@ -269,9 +295,16 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             for (int u = 5; u >= 0; u--) {
                 const int i = base + u;
                 const double* Ui = ust + (size_t)i * UST;
+#ifdef FRX_EXACT
+                double acc = Ui[7 + d];
+#pragma unroll
+                for (int t = 6; t >= 1; t--) acc -= Ui[t] * w[(u + t) % 6];
+                acc = acc / Ui[0];
+#else
                 double acc = Ui[6 + d];
 #pragma unroll
                 for (int t = 6; t >= 1; t--) acc -= Ui[t - 1] * w[(u + t) % 6];
+#endif
                 w[u] = acc;
                 cg_[3 * i + d] = acc;
             }
@@ -544,6 +577,233 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
     }
 }
 
+#ifdef FRX_EXACT
+// K2 (reference-order build) -----------------------------------------------------------------------
+// One THREAD per trajectory, every loop sequential, every expression in the reference's order
+// (MINCO_S3::addTimeIntPenalty CPU.hpp:188-408 with the Jacobians dxB/dyB/dzB materialised, getTrajJerkCost :507,
+// addGradJbyT :65, addGradJbyC :80): the accumulators gdC / gdT / pena receive their terms in exactly the sequence
+// the reference adds them, so the result is bit-identical to the CPU code.  Slow by construction; validation only.
+__device__ __forceinline__ double ex_dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ double ex_sq3(const double* a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
+__device__ __forceinline__ void ex_cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void ex_normalizeFDF(const double* x, double* xNor, double* G) {  // CPU.hpp:163-185, G row-major
+    const double a = x[0], b = x[1], c = x[2];
+    const double aSqr = a * a, bSqr = b * b, cSqr = c * c;
+    const double ab = a * b, bc = b * c, ca = c * a;
+    const double xSqrNorm = aSqr + bSqr + cSqr;
+    const double xNorm = sqrt(xSqrNorm);
+    const double den = xSqrNorm * xNorm;
+    xNor[0] = a / xNorm, xNor[1] = b / xNorm, xNor[2] = c / xNorm;
+    G[0] = bSqr + cSqr, G[1] = -ab, G[2] = -ca;
+    G[3] = -ab, G[4] = aSqr + cSqr, G[5] = -bc;
+    G[6] = -ca, G[7] = -bc, G[8] = aSqr + bSqr;
+    for (int i = 0; i < 9; i++) G[i] /= den;
+}
+
+__global__ void __launch_bounds__(32) penalty_exact_kernel(BatchView bv) {
+    const int b = bv.sub_traj0 + blockIdx.x * 32 + threadIdx.x;
+    if (b >= bv.sub_traj1) return;
+    if (bv.active && !bv.active[b]) return;
+    const int p0 = bv.piece_off[b];
+    const int N = bv.piece_off[b + 1] - p0;
+    const DevParams P = bv.par[b];
+    const double vMaxSqr = P.vmax_sqr, thrAccMinSqr = P.thrmin_sqr, thrAccMaxSqr = P.thrmax_sqr, bdrMaxSqr = P.bdrmax_sqr;
+    const double* ell = P.ell;
+    const double* ci = P.chi;
+    double pena = 0.0;
+    for (int i = 0; i < N; i++) {
+        const int gp = p0 + i;
+        const double* c = bv.c + 18 * (size_t)gp;  // 6x3 block, c[3*k+d]
+        double* gc = bv.gdC + 18 * (size_t)gp;
+        const double T1 = bv.T[gp], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        const double *c3 = c + 9, *c4 = c + 12, *c5 = c + 15;
+        // energy, its time gradient and its coefficient gradient first (evalTrajCostGrad order, CPU.hpp:542-544)
+        bv.energy[gp] = 36.0 * ex_sq3(c3) * T1 + 144.0 * ex_dot3(c4, c3) * T2 + 192.0 * ex_sq3(c4) * T3 + 240.0 * ex_dot3(c5, c3) * T3 +
+                        720.0 * ex_dot3(c5, c4) * T4 + 720.0 * ex_sq3(c5) * T5;
+        double gdT = 0.0;
+        gdT += 36.0 * ex_sq3(c3) + 288.0 * ex_dot3(c4, c3) * T1 + 576.0 * ex_sq3(c4) * T2 + 720.0 * ex_dot3(c5, c3) * T2 +
+               2880.0 * ex_dot3(c5, c4) * T3 + 3600.0 * ex_sq3(c5) * T4;
+        for (int q = 0; q < 9; q++) gc[q] = 0.0;
+        for (int cc = 0; cc < 3; cc++) {
+            double g5 = 0.0, g4 = 0.0, g3 = 0.0;
+            g5 += 240.0 * c3[cc] * T3 + 720.0 * c4[cc] * T4 + 1440.0 * c5[cc] * T5;
+            g4 += 144.0 * c3[cc] * T2 + 384.0 * c4[cc] * T3 + 720.0 * c5[cc] * T4;
+            g3 += 72.0 * c3[cc] * T1 + 144.0 * c4[cc] * T2 + 240.0 * c5[cc] * T3;
+            gc[15 + cc] = g5, gc[12 + cc] = g4, gc[9 + cc] = g3;
+        }
+        const int cons = bv.cons[gp];
+        const double step = T1 / cons;
+        double s1 = 0.0;
+        const int innerLoop = cons + 1;
+        const double* faces = bv.faces + 6 * (size_t)bv.piece_face_off[gp];
+        const int K = bv.piece_face_cnt[gp];
+        for (int j = 0; j < innerLoop; j++) {
+            const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+            const double beta0[6] = {1.0, s1, s2, s3, s4, s5};
+            const double beta1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+            const double beta2[6] = {0.0, 0.0, 2.0, 6.0 * s1, 12.0 * s2, 20.0 * s3};
+            const double beta3[6] = {0.0, 0.0, 0.0, 6.0, 24.0 * s1, 60.0 * s2};
+            const double beta4[6] = {0.0, 0.0, 0.0, 0.0, 24.0, 120.0 * s1};
+            const double alpha = 1.0 / cons * j;
+            double pos[3], vel[3], acc[3], jer[3], sna[3];
+            for (int d = 0; d < 3; d++) {
+                double p = 0, v = 0, a = 0, jj = 0, sn = 0;
+                for (int k = 0; k < 6; k++) {
+                    p += c[3 * k + d] * beta0[k];
+                    v += c[3 * k + d] * beta1[k];
+                    a += c[3 * k + d] * beta2[k];
+                    jj += c[3 * k + d] * beta3[k];
+                    sn += c[3 * k + d] * beta4[k];
+                }
+                pos[d] = p, vel[d] = v, acc[d] = a, jer[d] = jj, sna[d] = sn;
+            }
+            const double h[3] = {acc[0], acc[1], acc[2] + P.gacc};
+            double zB[3], dzB[9];
+            ex_normalizeFDF(h, zB, dzB);
+            const double czB[3] = {0.0, zB[2], -zB[1]};
+            const double cdzB[9] = {0, 0, 0, dzB[6], dzB[7], dzB[8], -dzB[3], -dzB[4], -dzB[5]};
+            double yB[3], dnczB[9];
+            ex_normalizeFDF(czB, yB, dnczB);
+            double xB[3];
+            ex_cross3(yB, zB, xB);
+            double dyB[9];
+            for (int r = 0; r < 3; r++)
+                for (int cc = 0; cc < 3; cc++)
+                    dyB[3 * r + cc] = dnczB[3 * r + 0] * cdzB[0 + cc] + dnczB[3 * r + 1] * cdzB[3 + cc] + dnczB[3 * r + 2] * cdzB[6 + cc];
+            double dxB[9];
+            for (int m = 0; m < 3; m++) {
+                const double dy[3] = {dyB[m], dyB[3 + m], dyB[6 + m]};
+                const double dz[3] = {dzB[m], dzB[3 + m], dzB[6 + m]};
+                double t0[3], t1[3];
+                ex_cross3(dy, zB, t0);
+                ex_cross3(yB, dz, t1);
+                for (int r = 0; r < 3; r++) dxB[3 * r + m] = t0[r] + t1[r];
+            }
+            const double rotM[9] = {xB[0], yB[0], zB[0], xB[1], yB[1], zB[1], xB[2], yB[2], zB[2]};
+            double gradSdTxyz[9];
+            for (int r = 0; r < 3; r++) {
+                gradSdTxyz[3 * r + 0] = dxB[3 * r] * jer[0] + dxB[3 * r + 1] * jer[1] + dxB[3 * r + 2] * jer[2];
+                gradSdTxyz[3 * r + 1] = dyB[3 * r] * jer[0] + dyB[3 * r + 1] * jer[1] + dyB[3 * r + 2] * jer[2];
+                gradSdTxyz[3 * r + 2] = dzB[3 * r] * jer[0] + dzB[3 * r + 1] * jer[1] + dzB[3 * r + 2] * jer[2];
+            }
+            const double fThr = sqrt(ex_sq3(h));
+            const double dfThr[3] = {h[0] / fThr, h[1] / fThr, h[2] / fThr};
+            const double sqrMagThr = fThr * fThr;
+            const double dSqrMagThr[3] = {2 * h[0], 2 * h[1], 2 * h[2]};
+            double rotTrDotJer[3];
+            for (int r = 0; r < 3; r++) rotTrDotJer[r] = rotM[0 + r] * jer[0] + rotM[3 + r] * jer[1] + rotM[6 + r] * jer[2];
+            const double bdr[3] = {rotTrDotJer[0] / fThr, rotTrDotJer[1] / fThr, rotTrDotJer[2] / fThr};
+            const double xyBdr[3] = {-bdr[1], bdr[0], 0.0};
+            const double sqrMagBdr = ex_sq3(xyBdr);
+            double comb[9], dBdr[9];
+            for (int q = 0; q < 9; q++) comb[q] = dxB[q] * rotTrDotJer[0] + dyB[q] * rotTrDotJer[1] + dzB[q] * rotTrDotJer[2];
+            for (int r = 0; r < 3; r++)
+                for (int cc = 0; cc < 3; cc++) {
+                    const double first = (-rotTrDotJer[r]) * dfThr[cc] / (fThr * fThr);
+                    const double prod = rotM[0 + r] * comb[0 + cc] + rotM[3 + r] * comb[3 + cc] + rotM[6 + r] * comb[6 + cc];
+                    dBdr[3 * r + cc] = first - prod / fThr;
+                }
+            double dSqrMagBdr[3], dJerSqrMagBdr[3];
+            for (int cc = 0; cc < 3; cc++)
+                dSqrMagBdr[cc] = 2.0 * xyBdr[0] * (-dBdr[3 + cc]) + 2.0 * xyBdr[1] * dBdr[0 + cc] + 2.0 * xyBdr[2] * 0.0;
+            for (int cc = 0; cc < 3; cc++) {
+                const double r0 = rotM[3 * cc + 0] / fThr;
+                const double r1 = rotM[3 * cc + 1] / fThr;
+                dJerSqrMagBdr[cc] = 2.0 * xyBdr[0] * (-r1) + 2.0 * xyBdr[1] * r0 + 2.0 * xyBdr[2] * 0.0;
+            }
+            const double violaVel = ex_sq3(vel) - vMaxSqr;
+            const double violaThrl = thrAccMinSqr - sqrMagThr;
+            const double violaThrh = sqrMagThr - thrAccMaxSqr;
+            const double violaBdr = sqrMagBdr - bdrMaxSqr;
+            const double omg = (j == 0 || j == innerLoop - 1) ? 0.5 : 1.0;
+            for (int k = 0; k < K; k++) {
+                const double* on = faces + 6 * k;
+                const double* pt = on + 3;
+                double gradSdT[3];
+                for (int m = 0; m < 3; m++) gradSdT[m] = gradSdTxyz[0 + m] * on[0] + gradSdTxyz[3 + m] * on[1] + gradSdTxyz[6 + m] * on[2];
+                const double outerNormaldVel = ex_dot3(on, vel);
+                double eNormGd[3];
+                for (int m = 0; m < 3; m++) eNormGd[m] = (rotM[0 + m] * on[0] + rotM[3 + m] * on[1] + rotM[6 + m] * on[2]) * ell[m];
+                const double eNorm = sqrt(ex_sq3(eNormGd));
+                for (int m = 0; m < 3; m++) eNormGd[m] /= eNorm;
+                const double dp[3] = {pos[0] - pt[0], pos[1] - pt[1], pos[2] - pt[2]};
+                double signedDist = ex_dot3(on, dp) + eNorm;
+                for (int m = 0; m < 3; m++) eNormGd[m] *= ell[m];
+                signedDist += P.margin;
+                if (signedDist > 0) {
+                    const double signedDistSqr = signedDist * signedDist;
+                    const double signedDistCub = signedDist * signedDistSqr;
+                    const double fac = omg * step * ci[0] * 3.0 * signedDistSqr;
+                    for (int r = 0; r < 6; r++)
+                        for (int cc = 0; cc < 3; cc++) {
+                            const double gx = (beta2[r] * on[0]) * dxB[0 + cc] + (beta2[r] * on[1]) * dxB[3 + cc] + (beta2[r] * on[2]) * dxB[6 + cc];
+                            const double gy = (beta2[r] * on[0]) * dyB[0 + cc] + (beta2[r] * on[1]) * dyB[3 + cc] + (beta2[r] * on[2]) * dyB[6 + cc];
+                            const double gz = (beta2[r] * on[0]) * dzB[0 + cc] + (beta2[r] * on[1]) * dzB[3 + cc] + (beta2[r] * on[2]) * dzB[6 + cc];
+                            const double gradSdC = beta0[r] * on[cc] + gx * eNormGd[0] + gy * eNormGd[1] + gz * eNormGd[2];
+                            gc[3 * r + cc] += fac * gradSdC;
+                        }
+                    const double gradSignedDt = alpha * (outerNormaldVel + gradSdT[0] * eNormGd[0] + gradSdT[1] * eNormGd[1] + gradSdT[2] * eNormGd[2]);
+                    gdT += omg * ci[0] * (3.0 * signedDistSqr * gradSignedDt * step + signedDistCub / cons);
+                    pena += omg * step * ci[0] * signedDistCub;
+                }
+            }
+            if (violaVel > 0.0) {
+                double pd = violaVel * violaVel;
+                const double pn = pd * violaVel;
+                pd *= 3.0;
+                const double gradViolaVt = (2.0 * alpha * vel[0]) * acc[0] + (2.0 * alpha * vel[1]) * acc[1] + (2.0 * alpha * vel[2]) * acc[2];
+                const double fac = omg * step * ci[1] * pd;
+                for (int r = 0; r < 6; r++)
+                    for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (2.0 * beta1[r] * vel[cc]);
+                gdT += omg * (ci[1] * pd * gradViolaVt * step + ci[1] * pn / cons);
+                pena += omg * step * ci[1] * pn;
+            }
+            if (violaThrl > 0.0) {
+                double pd = violaThrl * violaThrl;
+                const double pn = pd * violaThrl;
+                pd *= 3.0;
+                const double gt = (-alpha * dSqrMagThr[0]) * jer[0] + (-alpha * dSqrMagThr[1]) * jer[1] + (-alpha * dSqrMagThr[2]) * jer[2];
+                const double fac = omg * step * ci[2] * pd;
+                for (int r = 0; r < 6; r++)
+                    for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (-beta2[r] * dSqrMagThr[cc]);
+                gdT += omg * (ci[2] * pd * gt * step + ci[2] * pn / cons);
+                pena += omg * step * ci[2] * pn;
+            }
+            if (violaThrh > 0.0) {
+                double pd = violaThrh * violaThrh;
+                const double pn = pd * violaThrh;
+                pd *= 3.0;
+                const double gt = (alpha * dSqrMagThr[0]) * jer[0] + (alpha * dSqrMagThr[1]) * jer[1] + (alpha * dSqrMagThr[2]) * jer[2];
+                const double fac = omg * step * ci[2] * pd;
+                for (int r = 0; r < 6; r++)
+                    for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (beta2[r] * dSqrMagThr[cc]);
+                gdT += omg * (ci[2] * pd * gt * step + ci[2] * pn / cons);
+                pena += omg * step * ci[2] * pn;
+            }
+            if (violaBdr > 0.0) {
+                double pd = violaBdr * violaBdr;
+                const double pn = pd * violaBdr;
+                pd *= 3.0;
+                const double gt = alpha * (ex_dot3(dSqrMagBdr, jer) + ex_dot3(dJerSqrMagBdr, sna));
+                const double fac = omg * step * ci[3] * pd;
+                for (int r = 0; r < 6; r++)
+                    for (int cc = 0; cc < 3; cc++) gc[3 * r + cc] += fac * (beta2[r] * dSqrMagBdr[cc] + beta3[r] * dJerSqrMagBdr[cc]);
+                gdT += omg * (ci[3] * pd * gt * step + ci[3] * pn / cons);
+                pena += omg * step * ci[3] * pn;
+            }
+            s1 += step;
+        }
+        bv.gdT[gp] = gdT;
+        bv.pen[gp] = 0.0;
+    }
+    bv.pen[p0] = pena;  // the single running accumulator of the reference (CPU.hpp:203,406): K3 adds N-1 exact zeros to it
+}
+#endif  // FRX_EXACT
+
 // K3 ---------------------------------------------------------------------------------------------
 // One trajectory per CTA of two warps.  The LU factors written by K1 (bv.lu, 16 doubles per row) are
 // streamed through a ring of 6-row blocks in shared memory: warp 1 issues cp.async copies LOOKAHEAD
@@ -657,7 +917,11 @@ __global__ void __launch_bounds__(64)
 #define UCOEF(u, s) (((u) - (s) >= 0) ? cur[((u) - (s)) * BW + 6 + (s)] : prv[((u) - (s) + 6) * BW + 6 + (s)])
 #define PRE1(u) (((((bs[3 * (u)] - UCOEF(u, 6) * w[((u) + 0) % 6]) - UCOEF(u, 5) * w[((u) + 1) % 6]) - UCOEF(u, 4) * w[((u) + 2) % 6]) - \
                   UCOEF(u, 3) * w[((u) + 3) % 6]) - UCOEF(u, 2) * w[((u) + 4) % 6])
+#ifdef FRX_EXACT
+#define FIN1(u, pre) (((pre)-UCOEF(u, 1) * w[((u) + 5) % 6]) / cur[(u) * BW + 6])
+#else
 #define FIN1(u, pre) (((pre)-UCOEF(u, 1) * w[((u) + 5) % 6]) * cur[(u) * BW + 6])
+#endif
     {
         double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // z_{i-6..i-1} of this lane's right-hand side: z_j at w[j mod 6]
         for (int p = 0; p < M; p++) {
@@ -892,6 +1156,7 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
         if (waste < best_waste) best_waste = waste, best_spt = spt;
     }
     pl.spt = best_spt;
+    if (const char* e = getenv("FRX_PEN_SPT")) pl.spt = atoi(e) > 0 ? atoi(e) : pl.spt;  // tuning override
     pl.tpp = (S + pl.spt - 1) / pl.spt;
     pl.threads = 64;
     pl.ppc = pl.threads / pl.tpp;
@@ -911,6 +1176,15 @@ cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem)
     return e;
 }
 
+static void launch_penalty(const BatchView& bv, const PenaltyLaunch& pl, cudaStream_t st) {
+#ifdef FRX_EXACT
+    penalty_exact_kernel<<<(bv.sub_traj1 - bv.sub_traj0 + 31) / 32, 32, 0, st>>>(bv);
+#else
+    const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
+    penalty_kernel<<<grid, pl.threads, pl.smem, st>>>(bv, pl);
+#endif
+}
+
 // One batched evaluation.  The banded kernels K1/K3 are latency-bound (a dependent chain per trajectory) and the
 // penalty kernel K2 is throughput-bound, so the batch is cut into sub-batches that are software-pipelined over two
 // streams: K1 of sub-batch i+1 runs under K2 of sub-batch i, K3 of sub-batch i under K2 of sub-batch i+1.
@@ -922,9 +1196,9 @@ cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl,
     const int B = bv0.B;
     if (nsub < 2 || B < 2 * nsub || !aux) {
         BatchView bv = bv0;
-        bv.sub_traj0 = 0, bv.sub_piece0 = 0, bv.sub_piece1 = bv.total_pieces;
+        bv.sub_traj0 = 0, bv.sub_traj1 = B, bv.sub_piece0 = 0, bv.sub_piece1 = bv.total_pieces;
         minco_forward_kernel<<<B, 64, fwd_smem, st>>>(bv, x_dev);
-        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bv, pl);
+        launch_penalty(bv, pl, st);
         minco_backward_kernel<<<B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
         return cudaGetLastError();
     }
@@ -933,15 +1207,14 @@ cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl,
     for (int i = 0; i < nsub; i++) {
         const int t0 = (int)((long long)B * i / nsub), t1 = (int)((long long)B * (i + 1) / nsub);
         BatchView bv = bv0;
-        bv.sub_traj0 = t0;
+        bv.sub_traj0 = t0, bv.sub_traj1 = t1;
         bv.sub_piece0 = piece_off_host[t0];
         bv.sub_piece1 = piece_off_host[t1];
         cudaStream_t s = (i & 1) ? aux : st;
         if (i == 1) cudaStreamWaitEvent(aux, ev_k1, 0);  // stagger: the second stream starts one K1 later
         minco_forward_kernel<<<t1 - t0, 64, fwd_smem, s>>>(bv, x_dev);
         if (i == 0) cudaEventRecord(ev_k1, st);
-        const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
-        penalty_kernel<<<grid, pl.threads, pl.smem, s>>>(bv, pl);
+        launch_penalty(bv, pl, s);
         minco_backward_kernel<<<t1 - t0, 64, bwd_smem, s>>>(bv, x_dev, cost_dev, grad_dev);
     }
     cudaEventRecord(ev_join, aux);
@@ -954,12 +1227,11 @@ cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl,
 cudaError_t launch_eval_window(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem, const double* x_dev,
                                double* cost_dev, double* grad_dev, cudaStream_t st, int t0, int t1, const int* piece_off_host) {
     BatchView bv = bv0;
-    bv.sub_traj0 = t0;
+    bv.sub_traj0 = t0, bv.sub_traj1 = t1;
     bv.sub_piece0 = piece_off_host[t0];
     bv.sub_piece1 = piece_off_host[t1];
     minco_forward_kernel<<<t1 - t0, 64, fwd_smem, st>>>(bv, x_dev);
-    const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
-    penalty_kernel<<<grid, pl.threads, pl.smem, st>>>(bv, pl);
+    launch_penalty(bv, pl, st);
     minco_backward_kernel<<<t1 - t0, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
     return cudaGetLastError();
 }
@@ -975,7 +1247,7 @@ cudaError_t launch_eval(const BatchView& bv0, const PenaltyLaunch& pl, size_t fw
 cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
                          const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms) {
     BatchView bvw = bv;
-    bvw.sub_traj0 = 0, bvw.sub_piece0 = 0, bvw.sub_piece1 = bv.total_pieces;
+    bvw.sub_traj0 = 0, bvw.sub_traj1 = bv.B, bvw.sub_piece0 = 0, bvw.sub_piece1 = bv.total_pieces;
     cudaEvent_t ev[4];
     for (auto& e : ev) cudaEventCreate(&e);
     ms[0] = ms[1] = ms[2] = 0.0;
@@ -984,7 +1256,7 @@ cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fw
         cudaEventRecord(ev[0], st);
         minco_forward_kernel<<<bv.B, 64, fwd_smem, st>>>(bvw, x_dev);
         cudaEventRecord(ev[1], st);
-        penalty_kernel<<<pl.grid, pl.threads, pl.smem, st>>>(bvw, pl);
+        launch_penalty(bvw, pl, st);
         cudaEventRecord(ev[2], st);
         minco_backward_kernel<<<bv.B, 64, bwd_smem, st>>>(bvw, x_dev, cost_dev, grad_dev);
         cudaEventRecord(ev[3], st);
@@ -1036,4 +1308,4 @@ double measure_fp64_tflops() {
     return best;
 }
 
-}  // namespace frx
+}  // namespace FRX_IMPL

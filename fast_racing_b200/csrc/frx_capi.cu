@@ -15,23 +15,25 @@
 #include "host_model.hpp"
 #include "solver.cuh"
 
-namespace frx {
-size_t forward_smem_bytes(int M, int coarseN);
-size_t backward_smem_bytes(int M, int coarseN);
-PenaltyLaunch plan_penalty(const BatchView& bv);
-cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);
-cudaError_t launch_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
-                        const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st);
-cudaError_t launch_eval_window(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem, const double* x_dev,
-                               double* cost_dev, double* grad_dev, cudaStream_t st, int t0, int t1, const int* piece_off_host);
-cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
-                                  const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, cudaStream_t aux,
-                                  cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,
-                                  int nsub);
-cudaError_t profile_eval(const BatchView& bv, const PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,
-                         const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);
-double measure_fp64_tflops();
-}  // namespace frx
+#define FRX_DECLARE_EVAL_API(NS)                                                                                                   \
+    namespace NS {                                                                                                                 \
+    size_t forward_smem_bytes(int M, int coarseN);                                                                                 \
+    size_t backward_smem_bytes(int M, int coarseN);                                                                                \
+    frx::PenaltyLaunch plan_penalty(const frx::BatchView& bv);                                                                     \
+    cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem);                                              \
+    cudaError_t launch_eval_window(const frx::BatchView& bv0, const frx::PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,      \
+                                   const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int t0, int t1,       \
+                                   const int* piece_off_host);                                                                     \
+    cudaError_t launch_eval_pipelined(const frx::BatchView& bv0, const frx::PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,   \
+                                      const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, cudaStream_t aux,  \
+                                      cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,      \
+                                      int nsub);                                                                                   \
+    cudaError_t profile_eval(const frx::BatchView& bv, const frx::PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,             \
+                             const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);      \
+    double measure_fp64_tflops();                                                                                                  \
+    }
+FRX_DECLARE_EVAL_API(frx_fast)
+FRX_DECLARE_EVAL_API(frx_exact)
 
 using namespace frx;
 
@@ -55,21 +57,33 @@ struct frx_batch {
     int max_M = 0, max_coarse = 0;
     BatchView bv{};
     PenaltyLaunch pl{};
-    size_t fwd_smem = 0, bwd_smem = 0;
+    size_t fwd_smem = 0, bwd_smem = 0;      // fast build
+    size_t fwd_smem_x = 0, bwd_smem_x = 0;  // reference-order build
+    bool exact = false;                      // frx_batch_set_reference_order
+    bool last_solver_exact = false;
     cudaStream_t stream = nullptr, aux = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_k1 = nullptr, ev_join = nullptr;
     int e2e_chunks = 2;  // chunks of the host-buffer path: copies of one chunk overlap the kernels of the other (FRX_E2E_CHUNKS)
     int nsub = 1;  // sub-batches of the pipelined evaluation (FRX_EVAL_SUBBATCHES); measured on B200: K2 fills the register
                    // file (8 CTAs x 64 thr x 128 regs), so K1/K3 cannot co-reside and pipelining only adds tails -> default off
     cudaError_t eval_on(const double* x, double* cost, double* grad, cudaStream_t st) {
-        return launch_eval_pipelined(bv, pl, fwd_smem, bwd_smem, x, cost, grad, st, aux, ev_fork, ev_k1, ev_join, piece_off.data(), nsub);
+        if (exact)
+            return frx_exact::launch_eval_pipelined(bv, pl, fwd_smem_x, bwd_smem_x, x, cost, grad, st, nullptr, nullptr, nullptr,
+                                                    nullptr, piece_off.data(), 1);
+        return frx_fast::launch_eval_pipelined(bv, pl, fwd_smem, bwd_smem, x, cost, grad, st, aux, ev_fork, ev_k1, ev_join,
+                                               piece_off.data(), nsub);
+    }
+    cudaError_t eval_window_on(const double* x, double* cost, double* grad, cudaStream_t st, int t0, int t1) {
+        if (exact) return frx_exact::launch_eval_window(bv, pl, fwd_smem_x, bwd_smem_x, x, cost, grad, st, t0, t1, piece_off.data());
+        return frx_fast::launch_eval_window(bv, pl, fwd_smem, bwd_smem, x, cost, grad, st, t0, t1, piece_off.data());
     }
     double last_ms = 0.0;
     std::vector<DevBuf> bufs;
     // persistent device-side x / cost / grad for the host-buffer API
     double *x_dev = nullptr, *g_dev = nullptr, *cost_dev = nullptr;
     double *x_pin = nullptr, *g_pin = nullptr, *cost_pin = nullptr;
-    SolverState* solver = nullptr;  // lazily created by frx_batch_optimize
+    frx_fast::SolverState* solver = nullptr;     // lazily created by frx_batch_optimize
+    frx_exact::SolverState* solver_x = nullptr;  // reference-order solver
     // result of the last optimize (for argmin)
     double* final_cost_dev = nullptr;
     bool have_final = false;
@@ -125,7 +139,8 @@ const char* frx_strerror(int s) {
 void frx_batch_destroy(frx_batch* b) {
     if (!b) return;
     cudaSetDevice(b->device);
-    if (b->solver) solver_destroy(b->solver);
+    if (b->solver) frx_fast::solver_destroy(b->solver);
+    if (b->solver_x) frx_exact::solver_destroy(b->solver_x);
     for (auto& d : b->bufs) d.release();
     if (b->x_pin) cudaFreeHost(b->x_pin);
     if (b->g_pin) cudaFreeHost(b->g_pin);
@@ -242,9 +257,11 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     BatchView& bv = b->bv;
     bv.B = B, bv.total_pieces = TP, bv.total_x = b->x_off[B];
     bv.max_faces = max_faces, bv.max_samples = max_samples;
-    b->fwd_smem = forward_smem_bytes(b->max_M, b->max_coarse);
-    b->bwd_smem = backward_smem_bytes(b->max_M, b->max_coarse);
-    if (b->fwd_smem > 227 * 1024 || b->bwd_smem > 227 * 1024) {
+    b->fwd_smem = frx_fast::forward_smem_bytes(b->max_M, b->max_coarse);
+    b->bwd_smem = frx_fast::backward_smem_bytes(b->max_M, b->max_coarse);
+    b->fwd_smem_x = frx_exact::forward_smem_bytes(b->max_M, b->max_coarse);
+    b->bwd_smem_x = frx_exact::backward_smem_bytes(b->max_M, b->max_coarse);
+    if (b->fwd_smem_x > 227 * 1024 || b->bwd_smem_x > 227 * 1024) {
         delete b;
         return FRX_ERR_CAPACITY;  // band system of one trajectory must fit the shared memory of one SM
     }
@@ -301,12 +318,13 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     if ((e = cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail(e, "event");
     if (const char* ns = getenv("FRX_EVAL_SUBBATCHES")) b->nsub = std::max(1, atoi(ns));
     if (const char* nc = getenv("FRX_E2E_CHUNKS")) b->e2e_chunks = std::max(1, atoi(nc));
-    b->pl = plan_penalty(bv);
+    b->pl = frx_fast::plan_penalty(bv);
     if (b->pl.smem > 227 * 1024) {
         frx_batch_destroy(b);
         return FRX_ERR_CAPACITY;
     }
-    if ((e = configure_kernels(b->fwd_smem, b->bwd_smem, b->pl.smem)) != cudaSuccess) return fail(e, "configure kernels");
+    if ((e = frx_fast::configure_kernels(b->fwd_smem, b->bwd_smem, b->pl.smem)) != cudaSuccess) return fail(e, "configure kernels");
+    if ((e = frx_exact::configure_kernels(b->fwd_smem_x, b->bwd_smem_x, b->pl.smem)) != cudaSuccess) return fail(e, "configure kernels (reference order)");
     *out = b;
     return FRX_OK;
 }
@@ -401,7 +419,7 @@ int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double
             const size_t o0 = (size_t)b->x_off[t0], o1 = (size_t)b->x_off[t1];
             cudaStream_t s = (c & 1) ? b->aux : b->stream;
             CK(cudaMemcpyAsync(b->x_dev + o0, b->x_pin + o0, sizeof(double) * (o1 - o0), cudaMemcpyHostToDevice, s));
-            CK(launch_eval_window(b->bv, b->pl, b->fwd_smem, b->bwd_smem, b->x_dev, b->cost_dev, b->g_dev, s, t0, t1, b->piece_off.data()));
+            CK(b->eval_window_on(b->x_dev, b->cost_dev, b->g_dev, s, t0, t1));
             CK(cudaMemcpyAsync(b->g_pin + o0, b->g_dev + o0, sizeof(double) * (o1 - o0), cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(b->cost_pin + t0, b->cost_dev + t0, sizeof(double) * (t1 - t0), cudaMemcpyDeviceToHost, s));
         }
@@ -442,7 +460,10 @@ int frx_batch_profile_eval(frx_batch* b, const double* x_dev, double* cost_dev, 
                            double* ms_out) {
     if (!b || !x_dev || !cost_dev || !grad_dev || !ms_out || reps < 1) return FRX_ERR_INVALID_ARG;
     CK(cudaSetDevice(b->device));
-    CK(profile_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
+    if (b->exact)
+        CK(frx_exact::profile_eval(b->bv, b->pl, b->fwd_smem_x, b->bwd_smem_x, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
+    else
+        CK(frx_fast::profile_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
     return FRX_OK;
 }
 // Launch geometry of the penalty kernel: out[6] = {samples/thread, threads/piece, pieces/CTA, CTA threads, grid, smem bytes}
@@ -452,7 +473,15 @@ int frx_batch_penalty_launch(const frx_batch* b, long long* out) {
     return FRX_OK;
 }
 // Measured fp64 FMA peak (TFLOP/s) of the current device: the secondary roofline of this path.
-double frx_measure_fp64_tflops(void) { return measure_fp64_tflops(); }
+double frx_measure_fp64_tflops(void) { return frx_fast::measure_fp64_tflops(); }
+
+// Reference-order mode: evaluation and solver in the reference's operation order (no FMA contraction, sequential
+// reductions, divisions as written): bit-identical to the CPU code, slow by construction (validation / reproducibility).
+int frx_batch_set_reference_order(frx_batch* b, int on) {
+    if (!b) return FRX_ERR_INVALID_ARG;
+    b->exact = on != 0;
+    return FRX_OK;
+}
 
 // Intermediate device quantities of the last evaluation (for component-level parity tests):
 // T[pieces], q[3*pieces] (last slot unused), c[18*pieces], gdC_lambda[18*pieces], pen[pieces], energy[pieces], gdT[pieces]
@@ -530,10 +559,15 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     std::vector<double> x0((size_t)b->bv.total_x);
     int s = frx_batch_initial_guess(b, x0.data());
     if (s != FRX_OK) return s;
-    if (!b->solver) {
-        s = solver_create(b->bv, b->x_off, &b->solver);
+    if (b->exact && !b->solver_x) {
+        s = frx_exact::solver_create(b->bv, b->x_off, &b->solver_x);
         if (s != FRX_OK) return s;
     }
+    if (!b->exact && !b->solver) {
+        s = frx_fast::solver_create(b->bv, b->x_off, &b->solver);
+        if (s != FRX_OK) return s;
+    }
+    b->last_solver_exact = b->exact;
     SolverIO io;
     io.x0_host = x0.data();
     io.rel_tol = rel_tol;
@@ -542,7 +576,7 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
         return b->eval_on(x_dev, cost_dev, grad_dev, st);
     };
     CK(cudaEventRecord(b->ev0, b->stream));
-    s = solver_run(b->solver, b->bv, io, eval);
+    s = b->exact ? frx_exact::solver_run(b->solver_x, b->bv, io, eval) : frx_fast::solver_run(b->solver, b->bv, io, eval);
     if (s != FRX_OK) return s;
     CK(cudaEventRecord(b->ev1, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -552,9 +586,11 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     // outputs
     const int B = b->bv.B;
     const size_t TP = b->bv.total_pieces;
-    s = solver_fetch(b->solver, final_cost, lbfgs_status, iterations, evaluations, x_final);
+    s = b->exact ? frx_exact::solver_fetch(b->solver_x, final_cost, lbfgs_status, iterations, evaluations, x_final)
+                 : frx_fast::solver_fetch(b->solver, final_cost, lbfgs_status, iterations, evaluations, x_final);
     if (s != FRX_OK) return s;
-    CK(cudaMemcpy(b->final_cost_dev, solver_final_cost_dev(b->solver), sizeof(double) * B, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(b->final_cost_dev, b->exact ? frx_exact::solver_final_cost_dev(b->solver_x) : frx_fast::solver_final_cost_dev(b->solver),
+                  sizeof(double) * B, cudaMemcpyDeviceToDevice));
     b->have_final = true;
     // final trajectory: the last forward pass of the solver was at the final iterate (solver_run
     // re-runs K1 on x_final, CPU.hpp:1258-1262), so T / c / energy are current.
@@ -589,14 +625,19 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     return FRX_OK;
 }
 
-int frx_batch_solver_ticks(const frx_batch* b) { return (b && b->solver) ? solver_ticks(b->solver) : 0; }
+int frx_batch_solver_ticks(const frx_batch* b) {
+    if (!b) return 0;
+    if (b->last_solver_exact) return b->solver_x ? frx_exact::solver_ticks(b->solver_x) : 0;
+    return b->solver ? frx_fast::solver_ticks(b->solver) : 0;
+}
 
 int frx_batch_argmin(frx_batch* b, int* best_traj, double* best_cost) {
     if (!b || !b->have_final) return FRX_ERR_INVALID_ARG;
     CK(cudaSetDevice(b->device));
     int idx = -1;
     double val = 0.0;
-    int s = solver_argmin(b->solver, b->final_cost_dev, b->bv.B, b->stream, &idx, &val);
+    int s = b->last_solver_exact ? frx_exact::solver_argmin(b->solver_x, b->final_cost_dev, b->bv.B, b->stream, &idx, &val)
+                                 : frx_fast::solver_argmin(b->solver, b->final_cost_dev, b->bv.B, b->stream, &idx, &val);
     if (s != FRX_OK) return s;
     if (best_traj) *best_traj = idx;
     if (best_cost) *best_cost = val;

@@ -5,10 +5,42 @@
 #include <cstdlib>
 #include <cstring>
 
-namespace frx {
+#ifdef FRX_EXACT
+#define FRX_IMPL frx_exact
+#else
+#define FRX_IMPL frx_fast
+#endif
+
+namespace FRX_IMPL {
+using namespace frx;
 
 #define UPD_THREADS 256
 
+#ifdef FRX_EXACT
+// Reference operation order: plain sequential sums (lbfgs.hpp:467-475), by one thread, broadcast through smem.
+__device__ __forceinline__ double block_dot(const double* __restrict__ a, const double* __restrict__ b, int n, double* red) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; i++) s += a[i] * b[i];
+        red[0] = s;
+    }
+    __syncthreads();
+    return red[0];
+}
+__device__ __forceinline__ void block_dot2(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                           const double* __restrict__ e, int n, double* red, double& r0, double& r1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int i = 0; i < n; i++) s0 += a[i] * b[i];
+        for (int i = 0; i < n; i++) s1 += c[i] * e[i];
+        red[0] = s0, red[1] = s1;
+    }
+    __syncthreads();
+    r0 = red[0], r1 = red[1];
+}
+#else
 // Deterministic CTA-wide dot product: strided per-thread partials, warp shuffle tree, then the 8
 // warp sums added in warp order.  (The reference sums sequentially, lbfgs.hpp:467-475; the
 // re-association is part of the stated fp64 tolerance, DESIGN.md "Numerics".)
@@ -54,6 +86,7 @@ __device__ __forceinline__ void block_dot2(const double* __restrict__ a, const d
     }
     r0 = t0, r1 = t1;
 }
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -534,6 +567,9 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
     {
         const char* e = getenv("FRX_LBFGS_TWO_LOOP");  // A/B switch: sequential two-loop in the reference's order
         sv.vector_free = (e && e[0] == '1') ? 0 : 1;
+#ifdef FRX_EXACT
+        sv.vector_free = 0;  // reference order: the sequential two-loop recursion of lbfgs.hpp:1359-1411
+#endif
     }
     const size_t nx = (size_t)bv.total_x;
     const size_t m = (size_t)sv.cfg.mem_size;
@@ -570,9 +606,33 @@ void solver_destroy(SolverState* s) {
     delete s;
 }
 
-SolverView& solver_view(SolverState* s) { return s->sv; }
+int solver_reset(SolverState* s, const SolverIO& io);
+cudaError_t solver_launch_update(SolverState* s, cudaStream_t st);
+int solver_poll_active(SolverState* s, cudaStream_t st, int* n_active);
+void solver_bind_active(BatchView& bv, SolverState* s, bool on);
+
+int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, const EvalFn& eval) {
+    int r = solver_reset(s, io);
+    if (r != FRX_OK) return r;
+    SolverView& sv = s->sv;
+    solver_bind_active(bv, s, true);
+    int ticks = 0, n_active = bv.B;
+    while (n_active > 0 && ticks < io.max_ticks) {
+        for (int t = 0; t < io.poll_every; t++) {
+            if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            ticks++;
+        }
+        r = solver_poll_active(s, io.stream, &n_active);
+        if (r != FRX_OK) return r;
+    }
+    s->ticks = ticks;
+    // final forward pass at the final iterates of ALL trajectories (CPU.hpp:1258-1262)
+    solver_bind_active(bv, s, false);
+    if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+    return FRX_OK;
+}
 int solver_ticks(SolverState* s) { return s->ticks; }
-void solver_set_ticks(SolverState* s, int t) { s->ticks = t; }
 const double* solver_final_cost_dev(SolverState* s) { return s->fx_dev; }
 void solver_bind_active(BatchView& bv, SolverState* s, bool on) { bv.active = on ? s->sv.active : nullptr; }
 
@@ -636,4 +696,4 @@ int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st
     return FRX_OK;
 }
 
-}  // namespace frx
+}  // namespace FRX_IMPL

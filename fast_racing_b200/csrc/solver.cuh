@@ -44,8 +44,6 @@ struct SolverView {
     int vector_free;               // 1: vector-free direction update (default); 0: sequential two-loop in the reference's order
 };
 
-struct SolverState;
-
 struct SolverIO {
     const double* x0_host = nullptr;
     double rel_tol = 1e-5;
@@ -54,41 +52,23 @@ struct SolverIO {
     int poll_every = 8;
 };
 
-int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverState** out);
-void solver_destroy(SolverState* s);
-SolverView& solver_view(SolverState* s);
-int solver_reset(SolverState* s, const SolverIO& io);                       // uploads x0, zeroes the state
-cudaError_t solver_launch_update(SolverState* s, cudaStream_t st);          // one lbfgs_update_kernel launch
-int solver_poll_active(SolverState* s, cudaStream_t st, int* n_active);     // sync + read the counter
-int solver_fetch(SolverState* s, double* final_cost, int* status, int* iters, int* evals, double* x_final);
-const double* solver_final_cost_dev(SolverState* s);
-int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st, int* idx, double* val);
-int solver_ticks(SolverState* s);
-void solver_set_ticks(SolverState* s, int t);
-void solver_bind_active(BatchView& bv, SolverState* s, bool on);
-
-// Runs the solve.  `eval(x_dev, cost_dev, grad_dev, stream)` launches one batched evaluation.
-template <class Eval>
-int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, Eval&& eval) {
-    int r = solver_reset(s, io);
-    if (r != FRX_OK) return r;
-    SolverView& sv = solver_view(s);
-    solver_bind_active(bv, s, true);
-    int ticks = 0, n_active = bv.B;
-    while (n_active > 0 && ticks < io.max_ticks) {
-        for (int t = 0; t < io.poll_every; t++) {
-            if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-            if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-            ticks++;
-        }
-        r = solver_poll_active(s, io.stream, &n_active);
-        if (r != FRX_OK) return r;
-    }
-    solver_set_ticks(s, ticks);
-    // final forward pass at the final iterates of ALL trajectories (CPU.hpp:1258-1262)
-    solver_bind_active(bv, s, false);
-    if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-    return FRX_OK;
-}
-
 }  // namespace frx
+
+#include <functional>
+
+// The solver is compiled twice (see build.py): namespace frx_fast (default) and frx_exact (reference operation order).
+#define FRX_DECLARE_SOLVER_API(NS)                                                                                          \
+    namespace NS {                                                                                                          \
+    struct SolverState;                                                                                                     \
+    typedef std::function<cudaError_t(const double*, double*, double*, cudaStream_t)> EvalFn;                               \
+    int solver_create(const frx::BatchView& bv, const std::vector<int>& x_off, SolverState** out);                          \
+    void solver_destroy(SolverState* s);                                                                                    \
+    /* Runs the solve: eval(x_dev, cost_dev, grad_dev, stream) launches one batched evaluation. */                          \
+    int solver_run(SolverState* s, frx::BatchView& bv, const frx::SolverIO& io, const EvalFn& eval);                        \
+    int solver_fetch(SolverState* s, double* final_cost, int* status, int* iters, int* evals, double* x_final);             \
+    const double* solver_final_cost_dev(SolverState* s);                                                                    \
+    int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st, int* idx, double* val);               \
+    int solver_ticks(SolverState* s);                                                                                       \
+    }
+FRX_DECLARE_SOLVER_API(frx_fast)
+FRX_DECLARE_SOLVER_API(frx_exact)

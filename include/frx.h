@@ -134,6 +134,12 @@ int frx_batch_optimize(frx_batch *b, double rel_tol, double *durations, double *
  * Device-side reduction; the cross-GPU gather is the caller's (NCCL all-gather of 16 B/rank). */
 int frx_batch_argmin(frx_batch *b, int *best_traj, double *best_cost);
 
+/* Reference-order mode (on != 0): evaluation and solver run in the reference's exact operation order — no FMA
+ * contraction, divisions as written, sequential reductions (the kernels are compiled a second time with --fmad=false,
+ * the penalty integral and the L-BFGS dot products run sequentially).  Results are bit-identical to the reference CPU
+ * code for the C2 time map; slow by construction — for validation and bit-reproducible regression runs. */
+int frx_batch_set_reference_order(frx_batch *b, int on);
+
 /* Device-time (ms, CUDA events on the batch stream) of the last eval / optimize call. */
 double frx_batch_last_ms(const frx_batch *b);
 

@@ -244,6 +244,59 @@ def test_solver_reference_tolerance_within_sensitivity_band(oracle_mod):
     batch.close()
 
 
+# ---- reference-order mode: bit-identical to the reference CPU code ---------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_reference_order_mode_is_bit_identical_to_reference(name):
+    """frx_batch_set_reference_order: the CUDA evaluation and the CUDA batched L-BFGS reproduce the golden vectors —
+    which are the outputs of the reference's own code (verbatim se3gcopter_cpu.hpp over the Eigen-API shim) — BIT FOR
+    BIT: cost, gradient, coefficients, and the whole solve at the reference's stopping tolerance (status, iteration and
+    evaluation counts, final x, final cost, durations)."""
+    p, z = load_golden(name)
+    batch = api.Batch([p])
+    batch.set_reference_order(True)
+    for i, x in enumerate(z["xs"]):
+        cost, grad = batch.eval(x)
+        assert cost[0] == z["ref_cost"][i] == z["cost"][i]
+        assert np.array_equal(grad, z["ref_grad"][i])
+        dbg = batch.debug_fetch()
+        assert np.array_equal(dbg["c"], z["c"][i]) and np.array_equal(dbg["T"], z["T"][i])
+    r = batch.optimize(float(z["opt_rel_tol"]))
+    assert r["status"][0] == int(z["opt_status"])
+    assert r["iterations"][0] == int(z["opt_iterations"]) and r["evaluations"][0] == int(z["opt_evaluations"])
+    assert np.array_equal(r["x"], z["opt_x"])
+    assert r["final_cost"][0] == float(z["opt_final_cost"])
+    assert np.array_equal(r["durations"], z["ref_opt_durations"])
+    assert np.array_equal(r["coeffs"], z["ref_opt_coeffs"])
+    assert r["jerk_cost"][0] == float(z["ref_opt_jerk_cost"])
+    batch.close()
+
+
+def test_reference_order_mode_batch_matches_oracle_bitwise(oracle_mod):
+    """A ragged batch (different M / F / K / parameter sets) in reference-order mode: every trajectory's solve equals the
+    oracle's bit for bit; the fast mode stays within the stated tolerance of it."""
+    probs = [synth.make_problem(81, 3, 8, 6), synth.make_problem(82, 7, np.array([6, 9, 12, 8, 7, 10, 6]), 9),
+             synth.make_problem(83, 5, 10, 12, params=api.MODERNCITY), synth.make_problem(84, 6, 12, 8, gates=(1, 3))]
+    batch = api.Batch(probs)
+    x = batch.initial_guess() + 0.3 * np.random.default_rng(2).normal(size=batch.total_x)
+    c_fast, g_fast = batch.eval(x)
+    batch.set_reference_order(True)
+    c_ex, g_ex = batch.eval(x)
+    r = batch.optimize(1e-5)
+    for i, o in _oracles(oracle_mod, batch, probs):
+        s = slice(batch.x_off[i], batch.x_off[i + 1])
+        f, g = o.eval(x[s])
+        assert c_ex[i] == f and np.array_equal(g_ex[s], g)
+        assert abs(c_fast[i] - f) <= COST_RTOL * abs(f) and rel_err(g_fast[s], g) <= GRAD_RTOL
+        ro = o.optimize(1e-5)
+        assert r["status"][i] == ro["status"] and r["iterations"][i] == ro["iterations"] and r["evaluations"][i] == ro["evaluations"]
+        assert np.array_equal(r["x"][s], ro["x"]) and r["final_cost"][i] == ro["final_cost"]
+        assert r["jerk_cost"][i] == ro["jerk_cost"]
+    batch.set_reference_order(False)
+    c2, g2 = batch.eval(x)
+    assert np.array_equal(c2, c_fast) and np.array_equal(g2, g_fast)
+    batch.close()
+
+
 def test_solver_statuses_and_masking(oracle_mod):
     """Trajectories of very different difficulty in one batch: early finishers are masked, all report a status."""
     probs = [synth.make_problem(70, 1, 8, 8), synth.make_problem(71, 3, 8, 8), synth.make_problem(72, 12, 12, 16)]
