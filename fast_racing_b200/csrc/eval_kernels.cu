@@ -387,13 +387,13 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
             const double alpha = invK * j;
             const double omg = (j == 0 || j == S - 1) ? 0.5 : 1.0;
             const double w = omg * step;
-            double pos[3], vel[3], ac[3], jer[3];
+            // Ordered to keep the live register set small: position + acceleration + frame first, then the face loop
+            // (only pos, the frame and the SFC accumulators are live), then velocity / jerk and the V, T, B penalties.
+            double pos[3], ac[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 pos[d] = ((((t[15 + d] * s1 + t[12 + d]) * s1 + t[9 + d]) * s1 + t[6 + d]) * s1 + t[3 + d]) * s1 + t[d];
-                vel[d] = (((t[30 + d] * s1 + t[27 + d]) * s1 + t[24 + d]) * s1 + t[21 + d]) * s1 + t[18 + d];
                 ac[d] = ((t[42 + d] * s1 + t[39 + d]) * s1 + t[36 + d]) * s1 + t[33 + d];
-                jer[d] = (t[51 + d] * s1 + t[48 + d]) * s1 + t[45 + d];
             }
             // body frame (CPU.hpp:266-279)
             const double hx = ac[0], hy = ac[1], hz = ac[2] + gacc;
@@ -406,11 +406,60 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
             const double yy = zz * inv_cn, yz = -zy * inv_cn;                 // yB = (0, yy, yz)
             const double xx = yy * zz - yz * zy, xy = yz * zx, xz = -yy * zx;  // xB = yB x zB
 
-            double g0[3] = {0, 0, 0}, g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, g3[3] = {0, 0, 0};
+            double g0[3] = {0, 0, 0};
             double uy[3] = {0, 0, 0}, uz[3] = {0, 0, 0};  // arguments of dyB^T and dzB^T
             double cst = 0.0, direct = 0.0;
             bool any = false, jac = false;
 
+            // ---- safe-flight-corridor faces (CPU.hpp:310-345) ----
+            if (chi0 != 0.0) {  // chi0 == 0 adds exact zeros in the reference
+                double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef * e_m * n
+                bool sfc_on = false;
+                for (int k = 0; k < F; k++) {
+                    const double2 f01 = *reinterpret_cast<const double2*>(faces + 6 * k);
+                    const double2 f23 = *reinterpret_cast<const double2*>(faces + 6 * k + 2);
+                    const double2 f45 = *reinterpret_cast<const double2*>(faces + 6 * k + 4);
+                    const double nx = f01.x, ny = f01.y, nz = f23.x;
+                    const double nd = nx * (pos[0] - f23.y) + ny * (pos[1] - f45.x) + nz * (pos[2] - f45.y);
+                    // |E R^T n| <= emax: faces farther than emax + margin cannot be active
+                    if (nd + margin + emax < -1.0e-9) continue;
+                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
+                    const double uyv = (yy * ny + yz * nz) * ey;
+                    const double uzv = (zx * nx + zy * ny + zz * nz) * ez;
+                    const double eNorm = sqrt(ux * ux + uyv * uyv + uzv * uzv);
+                    const double sd = nd + eNorm + margin;
+                    if (sd > 0.0) {
+                        const double sd2 = sd * sd, sd3 = sd * sd2;
+                        const double coef = w * chi0 * 3.0 * sd2;
+                        const double ie = 1.0 / eNorm;
+                        const double e0 = coef * (ux * ie * ex), e1 = coef * (uyv * ie * ey), e2 = coef * (uzv * ie * ez);
+                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
+                        ax[0] += e0 * nx, ax[1] += e0 * ny, ax[2] += e0 * nz;
+                        ay[0] += e1 * nx, ay[1] += e1 * ny, ay[2] += e1 * nz;
+                        az[0] += e2 * nx, az[1] += e2 * ny, az[2] += e2 * nz;
+                        cst += w * chi0 * sd3;
+                        direct += omg * chi0 * sd3 * invK;
+                        sfc_on = true;
+                    }
+                }
+                if (sfc_on) {
+                    // dxB^T ax + dyB^T ay + dzB^T az = dyB^T (ay + z x ax) + dzB^T (az + ax x y)
+                    uy[0] = ay[0] + (zy * ax[2] - zz * ax[1]);
+                    uy[1] = ay[1] + (zz * ax[0] - zx * ax[2]);
+                    uy[2] = ay[2] + (zx * ax[1] - zy * ax[0]);
+                    uz[0] = az[0] + (ax[1] * yz - ax[2] * yy);
+                    uz[1] = az[1] + (-ax[0] * yz);
+                    uz[2] = az[2] + (ax[0] * yy);
+                    any = true, jac = true;
+                }
+            }
+            double vel[3], jer[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                vel[d] = (((t[30 + d] * s1 + t[27 + d]) * s1 + t[24 + d]) * s1 + t[21 + d]) * s1 + t[18 + d];
+                jer[d] = (t[51 + d] * s1 + t[48 + d]) * s1 + t[45 + d];
+            }
+            double g1[3] = {0, 0, 0}, g2[3] = {0, 0, 0}, g3[3] = {0, 0, 0};
             // ---- velocity (CPU.hpp:347-359) ----
             const double violaVel = vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2] - vmax_sqr;
             if (violaVel > 0.0) {
@@ -451,56 +500,14 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
                     const double k0 = -coef * inv_f;
                     const double zwx = zy * wz - zz * wy, zwy = zz * wx - zx * wz, zwz = zx * wy - zy * wx;  // z x wv
                     const double wyx = wy * yz - wz * yy, wyy = -wx * yz, wyz = wx * yy;                      // wv x y
-                    uy[0] = k0 * (r0 * zwx + r1 * wx), uy[1] = k0 * (r0 * zwy + r1 * wy), uy[2] = k0 * (r0 * zwz + r1 * wz);
-                    uz[0] = k0 * (r0 * wyx + r2 * wx), uz[1] = k0 * (r0 * wyy + r2 * wy), uz[2] = k0 * (r0 * wyz + r2 * wz);
+                    uy[0] += k0 * (r0 * zwx + r1 * wx), uy[1] += k0 * (r0 * zwy + r1 * wy), uy[2] += k0 * (r0 * zwz + r1 * wz);
+                    uz[0] += k0 * (r0 * wyx + r2 * wx), uz[1] += k0 * (r0 * wyy + r2 * wy), uz[2] += k0 * (r0 * wyz + r2 * wz);
                     const double kh = -coef * hfac;
                     g2[0] += kh * hx, g2[1] += kh * hy, g2[2] += kh * hz;
                     const double kj = coef * inv_f;  // dJerSqrMagBdr = wv / f (CPU.hpp:297-299)
                     g3[0] = kj * wx, g3[1] = kj * wy, g3[2] = kj * wz;
                     cst += w * chi3 * v3;
                     direct += omg * chi3 * v3 * invK;
-                    any = true, jac = true;
-                }
-            }
-            // ---- safe-flight-corridor faces (CPU.hpp:310-345) ----
-            if (chi0 != 0.0) {  // chi0 == 0 adds exact zeros in the reference
-                double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef * e_m * n
-                bool sfc_on = false;
-                for (int k = 0; k < F; k++) {
-                    const double2 f01 = *reinterpret_cast<const double2*>(faces + 6 * k);
-                    const double2 f23 = *reinterpret_cast<const double2*>(faces + 6 * k + 2);
-                    const double2 f45 = *reinterpret_cast<const double2*>(faces + 6 * k + 4);
-                    const double nx = f01.x, ny = f01.y, nz = f23.x;
-                    const double nd = nx * (pos[0] - f23.y) + ny * (pos[1] - f45.x) + nz * (pos[2] - f45.y);
-                    // |E R^T n| <= emax: faces farther than emax + margin cannot be active
-                    if (nd + margin + emax < -1.0e-9) continue;
-                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
-                    const double uyv = (yy * ny + yz * nz) * ey;
-                    const double uzv = (zx * nx + zy * ny + zz * nz) * ez;
-                    const double eNorm = sqrt(ux * ux + uyv * uyv + uzv * uzv);
-                    const double sd = nd + eNorm + margin;
-                    if (sd > 0.0) {
-                        const double sd2 = sd * sd, sd3 = sd * sd2;
-                        const double coef = w * chi0 * 3.0 * sd2;
-                        const double ie = 1.0 / eNorm;
-                        const double e0 = coef * (ux * ie * ex), e1 = coef * (uyv * ie * ey), e2 = coef * (uzv * ie * ez);
-                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
-                        ax[0] += e0 * nx, ax[1] += e0 * ny, ax[2] += e0 * nz;
-                        ay[0] += e1 * nx, ay[1] += e1 * ny, ay[2] += e1 * nz;
-                        az[0] += e2 * nx, az[1] += e2 * ny, az[2] += e2 * nz;
-                        cst += w * chi0 * sd3;
-                        direct += omg * chi0 * sd3 * invK;
-                        sfc_on = true;
-                    }
-                }
-                if (sfc_on) {
-                    // dxB^T ax + dyB^T ay + dzB^T az = dyB^T (ay + z x ax) + dzB^T (az + ax x y)
-                    uy[0] += ay[0] + (zy * ax[2] - zz * ax[1]);
-                    uy[1] += ay[1] + (zz * ax[0] - zx * ax[2]);
-                    uy[2] += ay[2] + (zx * ax[1] - zy * ax[0]);
-                    uz[0] += az[0] + (ax[1] * yz - ax[2] * yy);
-                    uz[1] += az[1] + (-ax[0] * yz);
-                    uz[2] += az[2] + (ax[0] * yy);
                     any = true, jac = true;
                 }
             }
@@ -1148,12 +1155,15 @@ size_t backward_smem_bytes(int M, int coarseN) {
 PenaltyLaunch plan_penalty(const BatchView& bv) {
     PenaltyLaunch pl;
     const int S = bv.max_samples;
-    // samples per thread: aim for <= 16 threads per piece, pick the split that wastes fewest slots
-    int best_spt = (S + 15) / 16, best_waste = 1 << 30;
+    // samples per thread: aim for <= 16 threads per piece; among the candidates pick the split with the best combined
+    // efficiency = (used sample slots / allotted slots) x (used lanes / CTA lanes)   (S = K+1 is odd, so something is wasted)
+    int best_spt = (S + 15) / 16;
+    double best_eff = -1.0;
     for (int spt = (S + 15) / 16; spt <= (S + 15) / 16 + 2; spt++) {
         const int tpp = (S + spt - 1) / spt;
-        const int waste = tpp * spt - S;
-        if (waste < best_waste) best_waste = waste, best_spt = spt;
+        const int ppc = 64 / tpp > 0 ? 64 / tpp : 1;
+        const double eff = ((double)S / (tpp * spt)) * ((double)(ppc * tpp) / 64.0);
+        if (eff > best_eff + 1e-12) best_eff = eff, best_spt = spt;
     }
     pl.spt = best_spt;
     if (const char* e = getenv("FRX_PEN_SPT")) pl.spt = atoi(e) > 0 ? atoi(e) : pl.spt;  // tuning override
