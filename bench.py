@@ -283,6 +283,9 @@ def main():
         if world > 1:
             mine = torch.tensor([bc, float(rank * a.batch + bi)], dtype=torch.float64, device=dev)
             allv = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allv, mine)  # warm-up: the first collective of a shape pays NCCL's lazy channel set-up
+            torch.cuda.synchronize()
+            dist.barrier()
             torch.cuda.synchronize()
             g0 = time.perf_counter()
             dist.all_gather(allv, mine)

@@ -107,6 +107,21 @@ def test_eval_parity_ragged_batch(oracle_mod):
     _check_eval(oracle_mod, probs)
 
 
+def test_eval_parity_large_shapes(oracle_mod):
+    """Limits of the reference's CUDA path and beyond (cc.cuh:23-25: <= 100 pieces, <= 50 faces, <= 64 samples):
+    150 pieces, 50-face polytopes, 129 samples per piece."""
+    probs = [synth.make_problem(91, 150, 8, 4), synth.make_problem(92, 4, 50, 128), synth.make_problem(93, 100, np.full(100, 9), 6)]
+    _check_eval(oracle_mod, probs, sigmas=(0.0, 0.3))
+
+
+def test_capacity_limit_is_reported():
+    """The band system of one trajectory must fit one SM's shared memory: far beyond that, create() says so."""
+    p = synth.make_problem(94, 500, 6, 2)
+    with pytest.raises(api.FrxError) as e:
+        api.Batch([p])
+    assert e.value.status == api.FRX_ERR_CAPACITY
+
+
 def test_eval_parity_time_maps(oracle_mod):
     """Fixed total time (rho = 0) with the C2 and the exp diffeomorphism; soft time with exp."""
     p = synth.make_problem(41, 6, 10, 8)
