@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfrx.so")
+LIB_PATH = os.environ.get("FRX_LIB") or os.path.join(_HERE, "libfrx.so")  # FRX_LIB: instrumented debug variant
 
 FRX_OK = 0
 FRX_ERR_INVALID_ARG = -1

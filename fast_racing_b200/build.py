@@ -13,8 +13,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-OUT = os.path.join(HERE, "libfrx.so")
+# FRX_BUILD_TAG=dbg (with FRX_NVCC_EXTRA=...) builds an instrumented variant next to the product: libfrx_dbg.so
+_TAG = os.environ.get("FRX_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
+OUT = os.path.join(HERE, "libfrx" + ("_" + _TAG if _TAG else "") + ".so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-pthread", "-x", "cu"]
 # (source, object suffix, extra flags)
@@ -53,7 +55,7 @@ def build(force=False, verbose=False):
         srcp = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), newest_hdr):
             continue
-        cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("FRX_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", obj]
         procs.append((src + suffix, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for name, p in procs:

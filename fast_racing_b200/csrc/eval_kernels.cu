@@ -89,6 +89,32 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // CTA-wide barrier usable from warp-specialised branches (both warps of the 64-thread CTA arrive at barrier 1).
 __device__ __forceinline__ void cta_bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
+// Phase clocks (debug builds only: FRX_NVCC_EXTRA=-DFRX_PHASE_CLK): lane 0 of each warp of one CTA records clock64()
+// at phase boundaries; scripts/phase_clocks.py prints the differences.  Slot = kernel*32 + warp*16 + mark.
+__device__ long long g_phase_clk[96];
+#ifdef FRX_PHASE_CLK
+#define PHASE_MARK(kernel, mark)                                                                          \
+    do {                                                                                                  \
+        if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0)                                       \
+            g_phase_clk[(kernel)*32 + (threadIdx.x >> 5) * 16 + (mark)] = clock64();                      \
+    } while (0)
+#else
+#define PHASE_MARK(kernel, mark) \
+    do {                         \
+    } while (0)
+#endif
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Per-lane entry of the fill tables (lane e writes entry e of a junction / tail block).
 struct FillLane {
     int jr, js, jp, tr, ts, tp;
@@ -137,7 +163,7 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
     }
 }
 
-// smem: ring[RING][16] | scratch[32] | ust[N][9] (aliased by Tc[coarseN] during the prologue)
+// smem: ring[RING][16] | scratch[32] | ust[N][UST] (head aliased by Tc[coarseN] during the prologue, tail by the T/q staging)
 __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
     const int b = bv.sub_traj0 + blockIdx.x;
@@ -156,6 +182,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     double* scratch = ring + RING * BW;
     double* ust = scratch + 32;
     double* Tc = ust;  // coarse durations: dead before the first row is retired into ust
+    PHASE_MARK(0, 0);
 
     // ---- forwardT (CPU.hpp:626-676) ----
     if (par.softT) {
@@ -175,32 +202,72 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     }
     __syncthreads();
     // ---- splitToFineT (CPU.hpp:930-944) + forwardP (CPU.hpp:729-747) ----
+    // T_g and q_g are also staged in the tail of `ust` for the ring fills: entry g is consumed at phase g-3, long before
+    // the retired rows (6*UST doubles per phase from the front) reach the tail.
+    double* stage = ust + (size_t)(6 * UST - 4) * M;
     for (int i = tid; i < M; i += 64) {
         const int pl = bv.piece_poly[p0 + i];
-        bv.T[p0 + i] = Tc[pl] / bv.intervals[co0 + pl];
-        if (i < M - 1) {
+        const double Tv = Tc[pl] / bv.intervals[co0 + pl];
+        bv.T[p0 + i] = Tv;
+        stage[4 * i] = Tv;
+    }
+#ifdef FRX_EXACT
+    for (int i = tid; i < M - 1; i += 64) {  // one thread per waypoint, sums in the reference's order
+        const int k = bv.wp_vert_cnt[p0 + i] - 1;
+        const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
+        const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
+        double sn = 0.0;
+#pragma unroll 8
+        for (int a = 0; a < k; a++) sn += xi[a] * xi[a];
+        const double sc = 2.0 / (1.0 + sn);
+        double qx = 0.0, qy = 0.0, qz = 0.0;
+#pragma unroll 4
+        for (int a = 0; a < k; a++) {
+            const double r = sc * xi[a];
+            const double rr = r * r;
+            qx += V[3 * (a + 1) + 0] * rr;
+            qy += V[3 * (a + 1) + 1] * rr;
+            qz += V[3 * (a + 1) + 2] * rr;
+        }
+        const double qv[3] = {qx + V[0], qy + V[1], qz + V[2]};
+        for (int d = 0; d < 3; d++) bv.q[3 * (size_t)(p0 + i) + d] = stage[4 * i + 1 + d] = qv[d];
+    }
+#else
+    {   // four lanes per waypoint (sector-sized coalesced reads of xi and V, many loads in flight), one pass:
+        //   q = v0 + sc^2 * sum_a V_{a+1} xi_a^2,  sc = 2 / (1 + |xi|^2)
+        const int grp = tid >> 2, l4 = tid & 3;
+        const unsigned gmask = 0xFu << (lane & ~3);
+        for (int i = grp; i < M - 1; i += 16) {
             const int k = bv.wp_vert_cnt[p0 + i] - 1;
             const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
             const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
-            double sn = 0.0;
-#pragma unroll 8
-            for (int a = 0; a < k; a++) sn += xi[a] * xi[a];
-            const double sc = 2.0 / (1.0 + sn);
-            double qx = 0.0, qy = 0.0, qz = 0.0;
+            double sn = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll 4
-            for (int a = 0; a < k; a++) {
-                const double r = sc * xi[a];
-                const double rr = r * r;
-                qx += V[3 * (a + 1) + 0] * rr;
-                qy += V[3 * (a + 1) + 1] * rr;
-                qz += V[3 * (a + 1) + 2] * rr;
+            for (int a = l4; a < k; a += 4) {
+                const double xa = xi[a], x2 = xa * xa;
+                sn += x2;
+                sx += V[3 * (a + 1) + 0] * x2;
+                sy += V[3 * (a + 1) + 1] * x2;
+                sz += V[3 * (a + 1) + 2] * x2;
             }
-            bv.q[3 * (size_t)(p0 + i) + 0] = qx + V[0];
-            bv.q[3 * (size_t)(p0 + i) + 1] = qy + V[1];
-            bv.q[3 * (size_t)(p0 + i) + 2] = qz + V[2];
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                sn += __shfl_xor_sync(gmask, sn, o);
+                sx += __shfl_xor_sync(gmask, sx, o);
+                sy += __shfl_xor_sync(gmask, sy, o);
+                sz += __shfl_xor_sync(gmask, sz, o);
+            }
+            const double sc = 2.0 / (1.0 + sn), sc2 = sc * sc;
+            if (l4 < 3) {
+                const double qd = V[l4] + sc2 * (l4 == 0 ? sx : (l4 == 1 ? sy : sz));
+                bv.q[3 * (size_t)(p0 + i) + l4] = qd;
+                stage[4 * i + 1 + l4] = qd;
+            }
         }
     }
-    __syncthreads();  // T and q (global) are read back below
+#endif
+    __syncthreads();  // the fills read the staged T and q
+    PHASE_MARK(0, 1);
 
     double* lug = bv.lu + (size_t)BW * 6 * p0;
     FillLane fl;
@@ -209,8 +276,8 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         fl.jr = JR[e], fl.js = JS[e], fl.jp = JP[e], fl.jc = JC[e];
         fl.tr = TR[t], fl.ts = TS[t], fl.tp = TP[t], fl.tc = TC[t];
     }
-    auto loadT = [&](int g) { return (g >= 0 && g < M) ? bv.T[p0 + g] : 1.0; };
-    auto loadq = [&](int g) { return (lane < 3 && g >= 0 && g < M - 1) ? bv.q[3 * (size_t)(p0 + g) + lane] : 0.0; };
+    auto loadT = [&](int g) { return (g >= 0 && g < M) ? stage[4 * g] : 1.0; };
+    auto loadq = [&](int g) { return (lane < 3 && g >= 0 && g < M - 1) ? stage[4 * g + 1 + lane] : 0.0; };
     // ---- ring prologue: head rows, block 0, block 1 ----
     if (warp == 0) {
         fill_block(ring, bv, b, M, -1, lane, fl, 1.0, 0.0);
@@ -224,6 +291,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 #endif
     __syncthreads();
 
+    PHASE_MARK(0, 2);
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
     if (warp == 0) {
         const int r = lane / 3, cg = lane - 3 * r;
@@ -280,9 +348,11 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             cta_bar64();
         }
     }
+    PHASE_MARK(0, 3);
     // ---- retire the last six rows ----
     if (warp == 1) retire_rows(ring, lug, ust, 6 * (M - 1), 6, lane);
     __syncthreads();
+    PHASE_MARK(0, 4);
 
     // ---- back substitution U x = y (trajectory.hpp:706-717), row-oriented: lane d < 3 of warp 0 owns
     //      right-hand side d and keeps the last six results in registers ----
@@ -310,6 +380,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             }
         }
     }
+    PHASE_MARK(0, 5);
 }
 
 // K2 ---------------------------------------------------------------------------------------------
@@ -336,7 +407,31 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
     double* fc = cf + (size_t)pl.ppc * CF;
     double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
 
-    // ---- stage: polynomial coefficient tables (c and its first four derivatives, per axis) and face lists ----
+    // per-thread operands, requested before the staging so that their latency overlaps it
+    const int pl_piece = tid / pl.tpp;
+    const int chunk = tid - pl_piece * pl.tpp;
+    bool mine = pl_piece < npieces;
+    int my_traj = 0, my_F = 0, my_K = 1;
+    double my_T = 1.0;
+    if (mine) {
+        const int gp = gp_base + pl_piece;
+        my_traj = bv.piece_traj[gp];
+        my_F = bv.piece_face_cnt[gp];
+        my_K = bv.cons[gp];
+        my_T = bv.T[gp];
+    }
+    // ---- stage: face lists (16-byte async copies, every piece of the CTA in flight at once) and polynomial
+    //      coefficient tables (c and its first four derivatives, per axis) ----
+    {
+        const int per = 3 * bv.max_faces;  // 16-byte chunks per piece slot (a face row = 48 B)
+        for (int i = tid; i < npieces * per; i += PEN_THREADS) {
+            const int p = i / per, e = i - p * per;
+            const int gp = gp_base + p;
+            if (e < 3 * bv.piece_face_cnt[gp])
+                cp_async16(fc + (size_t)p * 6 * bv.max_faces + 2 * e, bv.faces + 6 * (size_t)bv.piece_face_off[gp] + 2 * e);
+        }
+        cp_async_commit();
+    }
     for (int i = tid; i < npieces * 18; i += PEN_THREADS) {
         const int p = i / 18, e = i - 18 * p, k = e / 3, d = e - 3 * k;
         const double v = bv.c[18 * (size_t)gp_base + i];
@@ -347,30 +442,21 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
         if (k >= 3) t[45 + 3 * (k - 3) + d] = v * (double)(k * (k - 1) * (k - 2));            // jerk
         if (k >= 4) t[54 + 3 * (k - 4) + d] = v * (double)(k * (k - 1) * (k - 2) * (k - 3));  // snap
     }
-    for (int p = 0; p < npieces; p++) {
-        const int gp = gp_base + p;
-        const int nf = bv.piece_face_cnt[gp] * 6;
-        const double* src = bv.faces + 6 * (size_t)bv.piece_face_off[gp];
-        double* dst = fc + (size_t)p * 6 * bv.max_faces;
-        for (int i = tid; i < nf; i += PEN_THREADS) dst[i] = src[i];
-    }
 #pragma unroll
     for (int v = 0; v < 20; v++) part[v * PEN_THREADS + tid] = 0.0;
+    cp_async_wait<0>();
     __syncthreads();
 
-    const int pl_piece = tid / pl.tpp;
-    const int chunk = tid - pl_piece * pl.tpp;
     double* acc = part + tid;  // acc[v * PEN_THREADS]
 
-    if (pl_piece < npieces && !(bv.active && !bv.active[bv.piece_traj[gp_base + pl_piece]])) {
-        const int gp = gp_base + pl_piece;
-        const DevParams* __restrict__ P = bv.par + bv.piece_traj[gp];
+    if (mine && !(bv.active && !bv.active[my_traj])) {
+        const DevParams* __restrict__ P = bv.par + my_traj;
         const double* t = cf + (size_t)pl_piece * CF;
         const double* faces = fc + (size_t)pl_piece * 6 * bv.max_faces;
-        const int F = bv.piece_face_cnt[gp];
-        const int K = bv.cons[gp];
+        const int F = my_F;
+        const int K = my_K;
         const int S = K + 1;
-        const double step = bv.T[gp] / K;
+        const double step = my_T / K;
         const double invK = 1.0 / K;
         const int j0 = chunk * pl.spt;
         const int j1 = min(j0 + pl.spt, S);
@@ -415,31 +501,47 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
             if (chi0 != 0.0) {  // chi0 == 0 adds exact zeros in the reference
                 double ax[3] = {0, 0, 0}, ay[3] = {0, 0, 0}, az[3] = {0, 0, 0};  // sum coef * e_m * n
                 bool sfc_on = false;
-                for (int k = 0; k < F; k++) {
-                    const double2 f01 = *reinterpret_cast<const double2*>(faces + 6 * k);
-                    const double2 f23 = *reinterpret_cast<const double2*>(faces + 6 * k + 2);
-                    const double2 f45 = *reinterpret_cast<const double2*>(faces + 6 * k + 4);
-                    const double nx = f01.x, ny = f01.y, nz = f23.x;
-                    const double nd = nx * (pos[0] - f23.y) + ny * (pos[1] - f45.x) + nz * (pos[2] - f45.y);
-                    // |E R^T n| <= emax: faces farther than emax + margin cannot be active
-                    if (nd + margin + emax < -1.0e-9) continue;
-                    const double ux = (xx * nx + xy * ny + xz * nz) * ex;
-                    const double uyv = (yy * ny + yz * nz) * ey;
-                    const double uzv = (zx * nx + zy * ny + zz * nz) * ez;
-                    const double eNorm = sqrt(ux * ux + uyv * uyv + uzv * uzv);
-                    const double sd = nd + eNorm + margin;
-                    if (sd > 0.0) {
-                        const double sd2 = sd * sd, sd3 = sd * sd2;
-                        const double coef = w * chi0 * 3.0 * sd2;
-                        const double ie = 1.0 / eNorm;
-                        const double e0 = coef * (ux * ie * ex), e1 = coef * (uyv * ie * ey), e2 = coef * (uzv * ie * ez);
-                        g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
-                        ax[0] += e0 * nx, ax[1] += e0 * ny, ax[2] += e0 * nz;
-                        ay[0] += e1 * nx, ay[1] += e1 * ny, ay[2] += e1 * nz;
-                        az[0] += e2 * nx, az[1] += e2 * ny, az[2] += e2 * nz;
-                        cst += w * chi0 * sd3;
-                        direct += omg * chi0 * sd3 * invK;
-                        sfc_on = true;
+                // Two passes per group of 32 faces: (1) every lane tests all faces (cheap, convergent) and records the
+                // near ones in a bit mask; (2) each lane walks its own near faces, so a warp iterates max-over-lanes
+                // near-face counts instead of once per face that is near for ANY lane.  Ascending face order is kept.
+                for (int k0 = 0; k0 < F; k0 += 32) {
+                    const int kn = min(32, F - k0);
+                    unsigned near = 0u;
+                    for (int k = 0; k < kn; k++) {
+                        const double* fk = faces + 6 * (k0 + k);
+                        const double2 f01 = *reinterpret_cast<const double2*>(fk);
+                        const double2 f23 = *reinterpret_cast<const double2*>(fk + 2);
+                        const double2 f45 = *reinterpret_cast<const double2*>(fk + 4);
+                        const double nd = f01.x * (pos[0] - f23.y) + f01.y * (pos[1] - f45.x) + f23.x * (pos[2] - f45.y);
+                        // |E R^T n| <= emax: faces farther than emax + margin cannot be active
+                        if (!(nd + margin + emax < -1.0e-9)) near |= 1u << k;
+                    }
+                    while (near) {
+                        const double* fk = faces + 6 * (k0 + __ffs(near) - 1);
+                        near &= near - 1u;
+                        const double2 f01 = *reinterpret_cast<const double2*>(fk);
+                        const double2 f23 = *reinterpret_cast<const double2*>(fk + 2);
+                        const double2 f45 = *reinterpret_cast<const double2*>(fk + 4);
+                        const double nx = f01.x, ny = f01.y, nz = f23.x;
+                        const double nd = nx * (pos[0] - f23.y) + ny * (pos[1] - f45.x) + nz * (pos[2] - f45.y);
+                        const double ux = (xx * nx + xy * ny + xz * nz) * ex;
+                        const double uyv = (yy * ny + yz * nz) * ey;
+                        const double uzv = (zx * nx + zy * ny + zz * nz) * ez;
+                        const double eNorm = sqrt(ux * ux + uyv * uyv + uzv * uzv);
+                        const double sd = nd + eNorm + margin;
+                        if (sd > 0.0) {
+                            const double sd2 = sd * sd, sd3 = sd * sd2;
+                            const double coef = w * chi0 * 3.0 * sd2;
+                            const double ie = 1.0 / eNorm;
+                            const double e0 = coef * (ux * ie * ex), e1 = coef * (uyv * ie * ey), e2 = coef * (uzv * ie * ez);
+                            g0[0] += coef * nx, g0[1] += coef * ny, g0[2] += coef * nz;
+                            ax[0] += e0 * nx, ax[1] += e0 * ny, ax[2] += e0 * nz;
+                            ay[0] += e1 * nx, ay[1] += e1 * ny, ay[2] += e1 * nz;
+                            az[0] += e2 * nx, az[1] += e2 * ny, az[2] += e2 * nz;
+                            cst += w * chi0 * sd3;
+                            direct += omg * chi0 * sd3 * invK;
+                            sfc_on = true;
+                        }
                     }
                 }
                 if (sfc_on) {
@@ -826,16 +928,6 @@ __global__ void __launch_bounds__(32) penalty_exact_kernel(BatchView bv) {
 #define LOOKAHEAD (NBLK - 2)  // blocks in flight ahead of the sweep
 #define BLKD (6 * BW)         // doubles per block
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int NPEND>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Issue the copy of block `blk` (rows 6*blk .. 6*blk+5) into its ring slot; blocks outside [0, M) are skipped.
 __device__ __forceinline__ void issue_block(double* ring, const double* lug, int blk, int M, int lane) {
     if (blk >= 0 && blk < M) {
@@ -869,7 +961,10 @@ __global__ void __launch_bounds__(64)
     double* gq = gT + M;
     double* gTc = gq + 3 * (size_t)M;
     double* em = gTc + coarseN;
-    int* ivs = reinterpret_cast<int*>(em + 2 * (size_t)M);
+    double* tfac = em + 2 * (size_t)M;  // d(T)/d(tau) of the time map, per polytope
+    int* ivs = reinterpret_cast<int*>(tfac + coarseN);
+    int* ioff = ivs + coarseN;  // first piece of each polytope (prefix sum of intervals)
+    PHASE_MARK(2, 0);
 
     const double* lug = bv.lu + (size_t)BW * 6 * p0;
     const double* cg_ = bv.c + 18 * (size_t)p0;
@@ -886,25 +981,56 @@ __global__ void __launch_bounds__(64)
         for (int e = lane; e < BLKD; e += 32) ring[(size_t)(NBLK - 1) * BLKD + e] = 0.0;  // block -1 (rows -6..-1) = zeros
         for (int blk = 0; blk < LOOKAHEAD; blk++) issue_block(ring, lug, blk, M, lane);
         cp_async_commit();
-        // while the copies fly: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988), sequential sums
+        // while the copies fly: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988).  The operands are
+        // gathered by all lanes; the three sums are sequential (reference order), one lane each.
         for (int i = lane; i < M; i += 32) {
             em[i] = bv.energy[p0 + i];
             em[M + i] = bv.pen[p0 + i];
         }
         for (int i = lane; i < coarseN; i += 32) ivs[i] = bv.intervals[co0 + i];
-        __syncwarp();
-        if (lane == 0) {
-            double e = 0.0, pn = 0.0;
-            for (int i = 0; i < M; i++) e += em[i];
-            for (int i = 0; i < M; i++) pn += em[M + i];
-            double sT = 0.0;
-            if (par.softT) {
-                for (int i = 0; i < coarseN; i++) sT += par.c2 ? c2_forward(x[i]) : exp(x[i]);
-            } else {
-                for (int i = 0; i < M; i++) sT += bv.T[p0 + i];  // fixed total time: rho = 0 anyway
+        if (par.softT) {
+            for (int i = lane; i < coarseN; i += 32) {  // time map and its derivative (CPU.hpp:639-641, 830-838)
+                const double t = x[i];
+                double Tv, dv;
+                if (par.c2) {
+                    Tv = c2_forward(t);
+                    if (t > 0)
+                        dv = t + 1.0;
+                    else {
+                        const double den = (0.5 * t - 1.0) * t + 1.0;
+                        dv = (1.0 - t) / (den * den);
+                    }
+                } else {
+                    Tv = exp(t);
+                    dv = Tv;
+                }
+                gTc[i] = Tv;
+                tfac[i] = dv;
             }
-            cost_out[b] = (e + pn) + par.rho * sT;
+        } else {
+            for (int i = lane; i < M; i += 32) gT[i] = bv.T[p0 + i];  // fixed total time: rho = 0 anyway
         }
+        __syncwarp();
+        double part = 0.0;
+        if (lane == 0) {
+            for (int i = 0; i < M; i++) part += em[i];
+        } else if (lane == 1) {
+            for (int i = 0; i < M; i++) part += em[M + i];
+        } else if (lane == 2) {
+            if (par.softT) {
+                for (int i = 0; i < coarseN; i++) part += gTc[i];
+            } else {
+                for (int i = 0; i < M; i++) part += gT[i];
+            }
+        } else if (lane == 3) {
+            int o = 0;
+            for (int i = 0; i < coarseN; i++) {
+                ioff[i] = o;
+                o += ivs[i];
+            }
+        }
+        const double pn = __shfl_sync(0xffffffffu, part, 1), sT = __shfl_sync(0xffffffffu, part, 2);
+        if (lane == 0) cost_out[b] = (part + pn) + par.rho * sT;
         // pull x and the vertex range of this trajectory towards L2 for addLayerPGrad
         for (int o = lane * 16; o < nx; o += 32 * 16) prefetch_l2(x + o);
         if (M > 1) {
@@ -915,9 +1041,13 @@ __global__ void __launch_bounds__(64)
         cp_async_wait<0>();
     } else {
         const double* gdC = bv.gdC + 18 * (size_t)p0;
-        for (int i = lane; i < 3 * N; i += 32) Bs[i] = gdC[i];
+        for (int e = lane; e < 3 * N / 2; e += 32) cp_async16(Bs + 2 * e, gdC + 2 * e);  // 3N doubles, 16-byte aligned both sides
+        cp_async_commit();
+        cp_async_wait<0>();
     }
+    PHASE_MARK(2, 1);
     __syncthreads();
+    PHASE_MARK(2, 2);
 
     // ---- sweep 1: U^T z = b, ascending rows.  Phase p = rows 6p..6p+5 reads blocks p-1 and p. ----
     // coefficient u_{i-s,i} = row (i-s), slot 6+s; update order = ascending j = i-s, i.e. s = 6..1.
@@ -967,6 +1097,7 @@ __global__ void __launch_bounds__(64)
 #undef UCOEF
 #undef PRE1
 #undef FIN1
+    PHASE_MARK(2, 3);
     // ---- transition: the ring now holds blocks M-NBLK..M-1; block M (rows >= N) must read as zeros ----
     if (warp == 1) {
         cp_async_wait<0>();
@@ -1016,6 +1147,7 @@ __global__ void __launch_bounds__(64)
 #undef LCOEF
 #undef PRE2
 #undef FIN2
+    PHASE_MARK(2, 4);
     // ---- addPropCtoT (CPU.hpp:104-151), addPropCtoP (:154-161), rho (:989) ----
     for (int i = tid; i < M; i += 64) {
         if (i != tid) {  // pieces beyond the first 64: not prefetched
@@ -1051,70 +1183,60 @@ __global__ void __launch_bounds__(64)
             for (int d = 0; d < 3; d++) gq[3 * i + d] = Bs[3 * (6 * i + 5) + d];
     }
     __syncthreads();
-    // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope ----
-    if (tid == 0) {
-        int offset = 0;
-        for (int i = 0; i < coarseN; i++) {
-            const int iv = ivs[i];
-            double s = 0.0;
-            for (int a = 0; a < iv; a++) s += gT[offset + a];
-            gTc[i] = s / iv;
-            offset += iv;
+    PHASE_MARK(2, 5);
+    // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope; one thread per polytope ----
+    for (int i = tid; i < coarseN; i += 64) {
+        const int iv = ivs[i], offset = ioff[i];
+        double sgt = 0.0;
+        for (int a = 0; a < iv; a++) sgt += gT[offset + a];
+        const double gm = sgt / iv;
+        // ---- addLayerTGrad (CPU.hpp:816-894), free total time: the factor was computed in the prologue ----
+        if (par.softT) {
+            if (i < dimT) grad[i] = gm * tfac[i];
+        } else
+            gTc[i] = gm;
+    }
+    if (!par.softT) {
+        __syncthreads();
+        if (tid == 0) {
+            const int Ms1 = dimT;
+            const double gTail = par.sumT * gTc[Ms1];
+            double expTauSum = 0.0, gFreeDotExpTau = 0.0;
+            for (int i = 0; i < Ms1; i++) {
+                const double t = x[i];
+                const double gFree = par.sumT * gTc[i];
+                double eTau;
+                if (par.c2) {
+                    if (t > 0)
+                        eTau = (0.5 * t + 1.0) * t + 1.0;
+                    else
+                        eTau = 1.0 / ((0.5 * t - 1.0) * t + 1.0);
+                } else
+                    eTau = exp(t);
+                expTauSum += eTau;
+                gFreeDotExpTau += eTau * gFree;
+            }
+            const double den = expTauSum + 1.0;
+            for (int i = 0; i < Ms1; i++) {
+                const double t = x[i];
+                const double gFree = par.sumT * gTc[i];
+                double dE;
+                if (par.c2) {
+                    if (t > 0)
+                        dE = t + 1.0;
+                    else {
+                        const double ds = (0.5 * t - 1.0) * t + 1.0;
+                        dE = (1.0 - t) / (ds * ds);
+                    }
+                } else
+                    dE = exp(t);
+                grad[i] = (gFree - gTail) * dE / den - (gFreeDotExpTau - gTail * expTauSum) * dE / (den * den);
+            }
         }
     }
-    __syncthreads();
-    // ---- addLayerTGrad (CPU.hpp:816-894) ----
-    if (par.softT) {
-        for (int i = tid; i < dimT; i += 64) {
-            const double t = x[i];
-            double g = gTc[i];
-            if (par.c2) {
-                if (t > 0)
-                    g *= t + 1.0;
-                else {
-                    const double den = (0.5 * t - 1.0) * t + 1.0;
-                    g *= (1.0 - t) / (den * den);
-                }
-            } else
-                g *= exp(t);
-            grad[i] = g;
-        }
-    } else if (tid == 0) {
-        const int Ms1 = dimT;
-        const double gTail = par.sumT * gTc[Ms1];
-        double expTauSum = 0.0, gFreeDotExpTau = 0.0;
-        for (int i = 0; i < Ms1; i++) {
-            const double t = x[i];
-            const double gFree = par.sumT * gTc[i];
-            double eTau;
-            if (par.c2) {
-                if (t > 0)
-                    eTau = (0.5 * t + 1.0) * t + 1.0;
-                else
-                    eTau = 1.0 / ((0.5 * t - 1.0) * t + 1.0);
-            } else
-                eTau = exp(t);
-            expTauSum += eTau;
-            gFreeDotExpTau += eTau * gFree;
-        }
-        const double den = expTauSum + 1.0;
-        for (int i = 0; i < Ms1; i++) {
-            const double t = x[i];
-            const double gFree = par.sumT * gTc[i];
-            double dE;
-            if (par.c2) {
-                if (t > 0)
-                    dE = t + 1.0;
-                else {
-                    const double ds = (0.5 * t - 1.0) * t + 1.0;
-                    dE = (1.0 - t) / (ds * ds);
-                }
-            } else
-                dE = exp(t);
-            grad[i] = (gFree - gTail) * dE / den - (gFreeDotExpTau - gTail * expTauSum) * dE / (den * den);
-        }
-    }
+    PHASE_MARK(2, 6);
     // ---- addLayerPGrad (CPU.hpp:897-928) ----
+#ifdef FRX_EXACT
     for (int i = tid; i < M - 1; i += 64) {
         const int k = bv.wp_vert_cnt[p0 + i] - 1;
         const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
@@ -1139,6 +1261,42 @@ __global__ void __launch_bounds__(64)
             gxi[a] = gd * 2.0 / q1 - xi[a] * 4.0 * gdot / q1s;
         }
     }
+#else
+    {   // four lanes per waypoint, one accumulation pass:  with s_a = V_{a+1}.gq,  q1 = 1 + |xi|^2,  sg = sum_a s_a xi_a^2:
+        //   gd_a = 4 s_a xi_a / q1,  gdot = 4 sg / q1,  d/dxi_a = xi_a (8 s_a / q1^2 - 16 sg / q1^3)
+        const int grp = tid >> 2, l4 = tid & 3;
+        const unsigned gmask = 0xFu << (lane & ~3);
+        for (int i = grp; i < M - 1; i += 16) {
+            const int k = bv.wp_vert_cnt[p0 + i] - 1;
+            const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i] + 3;
+            const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
+            double* gxi = grad + dimT + bv.wp_xi_off[p0 + i];
+            const double gx = gq[3 * i], gy = gq[3 * i + 1], gz = gq[3 * i + 2];
+            double sn = 0.0, sg = 0.0;
+#pragma unroll 4
+            for (int a = l4; a < k; a += 4) {
+                const double xa = xi[a], x2 = xa * xa;
+                const double sa = V[3 * a] * gx + V[3 * a + 1] * gy + V[3 * a + 2] * gz;
+                sn += x2;
+                sg += sa * x2;
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                sn += __shfl_xor_sync(gmask, sn, o);
+                sg += __shfl_xor_sync(gmask, sg, o);
+            }
+            const double iq = 1.0 / (1.0 + sn), iq2 = iq * iq;
+            const double c1 = 8.0 * iq2, c2 = 16.0 * sg * iq2 * iq;
+#pragma unroll 4
+            for (int a = l4; a < k; a += 4) {
+                const double xa = xi[a];
+                const double sa = V[3 * a] * gx + V[3 * a + 1] * gy + V[3 * a + 2] * gz;
+                gxi[a] = xa * (c1 * sa - c2);
+            }
+        }
+    }
+#endif
+    PHASE_MARK(2, 7);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1149,7 +1307,7 @@ size_t forward_smem_bytes(int M, int coarseN) {
     return sizeof(double) * ((size_t)RING * BW + 32 + (ust > tc ? ust : tc));
 }
 size_t backward_smem_bytes(int M, int coarseN) {
-    return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + (coarseN + 2) / 2 + 1);
+    return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + coarseN + (coarseN + 1) + 1);
 }
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
@@ -1318,4 +1476,5 @@ double measure_fp64_tflops() {
     return best;
 }
 
+cudaError_t fetch_phase_clocks(long long* out96) { return cudaMemcpyFromSymbol(out96, g_phase_clk, sizeof(long long) * 96); }
 }  // namespace FRX_IMPL

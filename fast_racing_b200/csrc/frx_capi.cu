@@ -31,6 +31,7 @@
     cudaError_t profile_eval(const frx::BatchView& bv, const frx::PenaltyLaunch& pl, size_t fwd_smem, size_t bwd_smem,             \
                              const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);      \
     double measure_fp64_tflops();                                                                                                  \
+    cudaError_t fetch_phase_clocks(long long* out96);                                                                              \
     }
 FRX_DECLARE_EVAL_API(frx_fast)
 FRX_DECLARE_EVAL_API(frx_exact)
@@ -464,6 +465,12 @@ int frx_batch_profile_eval(frx_batch* b, const double* x_dev, double* cost_dev, 
         CK(frx_exact::profile_eval(b->bv, b->pl, b->fwd_smem_x, b->bwd_smem_x, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
     else
         CK(frx_fast::profile_eval(b->bv, b->pl, b->fwd_smem, b->bwd_smem, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
+    return FRX_OK;
+}
+// Debug builds (-DFRX_PHASE_CLK): clock64() marks of one CTA of K1 / K3 (zeros otherwise).
+int frx_debug_phase_clocks(long long* out96) {
+    if (!out96) return FRX_ERR_INVALID_ARG;
+    CK(frx_fast::fetch_phase_clocks(out96));
     return FRX_OK;
 }
 // Launch geometry of the penalty kernel: out[6] = {samples/thread, threads/piece, pieces/CTA, CTA threads, grid, smem bytes}

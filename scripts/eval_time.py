@@ -17,3 +17,5 @@ for k in range(20):
     e0.record(st); b.eval_device(xd.data_ptr(), cd.data_ptr(), gd.data_ptr(), st.cuda_stream); e1.record(st); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print(f"B={B} nsub={os.environ.get('FRX_EVAL_SUBBATCHES','default')}: {np.mean(ts)*1e3:.1f} us/eval (min {np.min(ts)*1e3:.1f}) -> {B/np.mean(ts)*1e3:.3e} evals/s; launches {b.eval_launches()}")
+ms = b.profile_eval(xd.data_ptr(), cd.data_ptr(), gd.data_ptr(), st.cuda_stream, 20)
+print("kernels us: K1 %.1f  K2 %.1f  K3 %.1f" % tuple(1e3 * v for v in ms))
