@@ -54,10 +54,12 @@ struct BatchView {
     const int* wp_vert_cnt;     // columns of the waypoint's V-polytope (k+1); 0 for the last slot
     const int* wp_xi_off;       // offset inside the xi block
     const double* faces;        // 6 * total faces
+    const float* faces_f32;     // 4 * total faces: (n, d_lo) in single precision for the conservative near-face prefilter of K2
     const double* verts;        // 3 * total vertex columns
     // work arrays (per piece unless noted)
     double* T;        // piece durations
     double* q;        // 3 per slot: inner waypoints
+    double* wpw;      // 4 per slot: (sum_a V_{a+1} xi_a^2, |xi|^2) of the waypoint map, reused by its gradient in K3
     double* c;        // 18 per piece: coefficient block rows 6i..6i+5, row-major (6x3)
     double* lu;       // 16 per row, 6 rows per piece: band LU factors (13 diagonals) + 3 unused
     double* gdC;      // 18 per piece: dJ/dc, becomes lambda after the adjoint solve

@@ -108,6 +108,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() {
@@ -184,6 +188,13 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     double* Tc = ust;  // coarse durations: dead before the first row is retired into ust
     PHASE_MARK(0, 0);
 
+    // waypoint index tables (free dimension, xi offset, vertex offset) staged next to Tc: one round trip instead of one per use
+    int* wpi = reinterpret_cast<int*>(ust + M + 1);
+    for (int i = tid; i < M - 1; i += 64) {
+        wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
+        wpi[M + i] = bv.wp_xi_off[p0 + i];
+        wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+    }
     // ---- forwardT (CPU.hpp:626-676) ----
     if (par.softT) {
         for (int i = tid; i < coarseN; i += 64) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
@@ -238,9 +249,9 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         const int grp = tid >> 2, l4 = tid & 3;
         const unsigned gmask = 0xFu << (lane & ~3);
         for (int i = grp; i < M - 1; i += 16) {
-            const int k = bv.wp_vert_cnt[p0 + i] - 1;
-            const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
-            const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
+            const int k = wpi[i];
+            const double* V = bv.verts + 3 * (size_t)wpi[2 * M + i];
+            const double* xi = x + dimT + wpi[M + i];
             double sn = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll 4
             for (int a = l4; a < k; a += 4) {
@@ -258,8 +269,10 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
                 sz += __shfl_xor_sync(gmask, sz, o);
             }
             const double sc = 2.0 / (1.0 + sn), sc2 = sc * sc;
+            const double sd_ = l4 == 0 ? sx : (l4 == 1 ? sy : sz);
+            bv.wpw[4 * (size_t)(p0 + i) + l4] = (l4 == 3) ? sn : sd_;  // reused by addLayerPGrad in K3
             if (l4 < 3) {
-                const double qd = V[l4] + sc2 * (l4 == 0 ? sx : (l4 == 1 ? sy : sz));
+                const double qd = V[l4] + sc2 * sd_;
                 bv.q[3 * (size_t)(p0 + i) + l4] = qd;
                 stage[4 * i + 1 + l4] = qd;
             }
@@ -406,20 +419,21 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
     double* cf = sm;
     double* fc = cf + (size_t)pl.ppc * CF;
     double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
+    float4* ff = reinterpret_cast<float4*>(part + 20 * PEN_THREADS);  // [ppc][max_faces] fp32 (n, d_lo) for the prefilter
+    double* Ts = reinterpret_cast<double*>(ff + (size_t)pl.ppc * bv.max_faces);  // [ppc] piece durations
 
     // per-thread operands, requested before the staging so that their latency overlaps it
     const int pl_piece = tid / pl.tpp;
     const int chunk = tid - pl_piece * pl.tpp;
     bool mine = pl_piece < npieces;
     int my_traj = 0, my_F = 0, my_K = 1;
-    double my_T = 1.0;
     if (mine) {
         const int gp = gp_base + pl_piece;
         my_traj = bv.piece_traj[gp];
         my_F = bv.piece_face_cnt[gp];
         my_K = bv.cons[gp];
-        my_T = bv.T[gp];
     }
+    if (tid < npieces) Ts[tid] = bv.T[gp_base + tid];
     // ---- stage: face lists (16-byte async copies, every piece of the CTA in flight at once) and polynomial
     //      coefficient tables (c and its first four derivatives, per axis) ----
     {
@@ -427,8 +441,9 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
         for (int i = tid; i < npieces * per; i += PEN_THREADS) {
             const int p = i / per, e = i - p * per;
             const int gp = gp_base + p;
-            if (e < 3 * bv.piece_face_cnt[gp])
-                cp_async16(fc + (size_t)p * 6 * bv.max_faces + 2 * e, bv.faces + 6 * (size_t)bv.piece_face_off[gp] + 2 * e);
+            const int cnt = bv.piece_face_cnt[gp], off = bv.piece_face_off[gp];
+            if (e < 3 * cnt) cp_async16(fc + (size_t)p * 6 * bv.max_faces + 2 * e, bv.faces + 6 * (size_t)off + 2 * e);
+            if (e < cnt) cp_async16(ff + (size_t)p * bv.max_faces + e, bv.faces_f32 + 4 * ((size_t)off + e));
         }
         cp_async_commit();
     }
@@ -453,10 +468,11 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
         const DevParams* __restrict__ P = bv.par + my_traj;
         const double* t = cf + (size_t)pl_piece * CF;
         const double* faces = fc + (size_t)pl_piece * 6 * bv.max_faces;
+        const float4* faces32 = ff + (size_t)pl_piece * bv.max_faces;
         const int F = my_F;
         const int K = my_K;
         const int S = K + 1;
-        const double step = my_T / K;
+        const double step = Ts[pl_piece] / K;
         const double invK = 1.0 / K;
         const int j0 = chunk * pl.spt;
         const int j1 = min(j0 + pl.spt, S);
@@ -465,6 +481,7 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
         for (int j = 0; j < j0 && j < S; j++) s1 += step;
         const double ex = P->ell[0], ey = P->ell[1], ez = P->ell[2];
         const double emax = fmax(ex, fmax(ey, ez));
+        const float reach32 = (float)(P->margin + emax + 1.0e-9) + 2.0e-6f;  // fp32 prefilter: margin + ellipsoid reach, rounded up
         const double chi0 = P->chi[0], chi1 = P->chi[1], chi2 = P->chi[2], chi3 = P->chi[3];
         const double margin = P->margin, gacc = P->gacc;
         const double vmax_sqr = P->vmax_sqr, thrmin_sqr = P->thrmin_sqr, thrmax_sqr = P->thrmax_sqr, bdrmax_sqr = P->bdrmax_sqr;
@@ -507,14 +524,16 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
                 for (int k0 = 0; k0 < F; k0 += 32) {
                     const int kn = min(32, F - k0);
                     unsigned near = 0u;
-                    for (int k = 0; k < kn; k++) {
-                        const double* fk = faces + 6 * (k0 + k);
-                        const double2 f01 = *reinterpret_cast<const double2*>(fk);
-                        const double2 f23 = *reinterpret_cast<const double2*>(fk + 2);
-                        const double2 f45 = *reinterpret_cast<const double2*>(fk + 4);
-                        const double nd = f01.x * (pos[0] - f23.y) + f01.y * (pos[1] - f45.x) + f23.x * (pos[2] - f45.y);
-                        // |E R^T n| <= emax: faces farther than emax + margin cannot be active
-                        if (!(nd + margin + emax < -1.0e-9)) near |= 1u << k;
+                    {   // conservative fp32 test on the (otherwise idle) fp32 pipe: t >= n.pos + margin + emax + 1e-9 and
+                        // d_lo <= n.p in exact arithmetic, so t < d_lo proves the fp64 early-out  nd + margin + emax < -1e-9;
+                        // everything else goes to the fp64 body, whose own  sd > 0  test decides (results unchanged).
+                        const float px = (float)pos[0], py = (float)pos[1], pz = (float)pos[2];
+                        const float bias = reach32 + 1.0e-6f * (fabsf(px) + fabsf(py) + fabsf(pz));
+                        for (int k = 0; k < kn; k++) {
+                            const float4 f = faces32[k0 + k];
+                            const float t = fmaf(f.x, px, fmaf(f.y, py, fmaf(f.z, pz, bias)));
+                            if (!(t < f.w)) near |= 1u << k;
+                        }
                     }
                     while (near) {
                         const double* fk = faces + 6 * (k0 + __ffs(near) - 1);
@@ -656,7 +675,7 @@ __global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, P
         double s = 0.0;
         for (int q = 0; q < pl.tpp; q++) s += src[q];
         const double* c = cf + (size_t)p * CF;
-        const double T1 = bv.T[gp], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+        const double T1 = Ts[p], T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
         if (v < 18) {
             // energy gradient w.r.t. c rows 3..5 (CPU.hpp:80-95), added first as in the reference
             const int row = v / 3, d = v - 3 * row;
@@ -964,6 +983,7 @@ __global__ void __launch_bounds__(64)
     double* tfac = em + 2 * (size_t)M;  // d(T)/d(tau) of the time map, per polytope
     int* ivs = reinterpret_cast<int*>(tfac + coarseN);
     int* ioff = ivs + coarseN;  // first piece of each polytope (prefix sum of intervals)
+    int* wpi = ioff + coarseN;  // per waypoint: free dimension k, xi offset, vertex offset (3 x M), for addLayerPGrad
     PHASE_MARK(2, 0);
 
     const double* lug = bv.lu + (size_t)BW * 6 * p0;
@@ -980,6 +1000,11 @@ __global__ void __launch_bounds__(64)
     if (warp == 1) {
         for (int e = lane; e < BLKD; e += 32) ring[(size_t)(NBLK - 1) * BLKD + e] = 0.0;  // block -1 (rows -6..-1) = zeros
         for (int blk = 0; blk < LOOKAHEAD; blk++) issue_block(ring, lug, blk, M, lane);
+        for (int i = lane; i < M - 1; i += 32) {
+            wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
+            wpi[M + i] = bv.wp_xi_off[p0 + i];
+            wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+        }
         cp_async_commit();
         // while the copies fly: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988).  The operands are
         // gathered by all lanes; the three sums are sequential (reference order), one lane each.
@@ -1262,36 +1287,31 @@ __global__ void __launch_bounds__(64)
         }
     }
 #else
-    {   // four lanes per waypoint, one accumulation pass:  with s_a = V_{a+1}.gq,  q1 = 1 + |xi|^2,  sg = sum_a s_a xi_a^2:
-        //   gd_a = 4 s_a xi_a / q1,  gdot = 4 sg / q1,  d/dxi_a = xi_a (8 s_a / q1^2 - 16 sg / q1^3)
+    {   // four lanes per waypoint, ONE streaming pass: with s_a = V_{a+1}.gq, q1 = 1 + |xi|^2 and W = sum_a V_{a+1} xi_a^2
+        // (both stored by K1):  gd_a = 4 s_a xi_a / q1,  gdot = 4 (W.gq) / q1,  d/dxi_a = xi_a (8 s_a / q1^2 - 16 (W.gq) / q1^3)
         const int grp = tid >> 2, l4 = tid & 3;
-        const unsigned gmask = 0xFu << (lane & ~3);
         for (int i = grp; i < M - 1; i += 16) {
-            const int k = bv.wp_vert_cnt[p0 + i] - 1;
-            const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i] + 3;
-            const double* xi = x + dimT + bv.wp_xi_off[p0 + i];
-            double* gxi = grad + dimT + bv.wp_xi_off[p0 + i];
+            const int k = wpi[i];
+            const double* V = bv.verts + 3 * ((size_t)wpi[2 * M + i] + 1);
+            const double* xi = x + dimT + wpi[M + i];
+            double* gxi = grad + dimT + wpi[M + i];
+            const double* ww = bv.wpw + 4 * (size_t)(p0 + i);
             const double gx = gq[3 * i], gy = gq[3 * i + 1], gz = gq[3 * i + 2];
-            double sn = 0.0, sg = 0.0;
-#pragma unroll 4
-            for (int a = l4; a < k; a += 4) {
-                const double xa = xi[a], x2 = xa * xa;
-                const double sa = V[3 * a] * gx + V[3 * a + 1] * gy + V[3 * a + 2] * gz;
-                sn += x2;
-                sg += sa * x2;
-            }
+            const double wg = ww[0] * gx + ww[1] * gy + ww[2] * gz;
+            const double iq = 1.0 / (1.0 + ww[3]), iq2 = iq * iq;
+            const double c1 = 8.0 * iq2, c2 = 16.0 * wg * iq2 * iq;
+            for (int a0 = l4; a0 < k; a0 += 20) {  // operands first (all loads in flight together), then the stores
+                double xa[5], va[5], vb[5], vc[5];
 #pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                sn += __shfl_xor_sync(gmask, sn, o);
-                sg += __shfl_xor_sync(gmask, sg, o);
-            }
-            const double iq = 1.0 / (1.0 + sn), iq2 = iq * iq;
-            const double c1 = 8.0 * iq2, c2 = 16.0 * sg * iq2 * iq;
-#pragma unroll 4
-            for (int a = l4; a < k; a += 4) {
-                const double xa = xi[a];
-                const double sa = V[3 * a] * gx + V[3 * a + 1] * gy + V[3 * a + 2] * gz;
-                gxi[a] = xa * (c1 * sa - c2);
+                for (int u = 0; u < 5; u++) {
+                    const int a = a0 + 4 * u;
+                    if (a < k) xa[u] = __ldg(xi + a), va[u] = __ldg(V + 3 * a), vb[u] = __ldg(V + 3 * a + 1), vc[u] = __ldg(V + 3 * a + 2);
+                }
+#pragma unroll
+                for (int u = 0; u < 5; u++) {
+                    const int a = a0 + 4 * u;
+                    if (a < k) gxi[a] = xa[u] * (c1 * (va[u] * gx + vb[u] * gy + vc[u] * gz) - c2);
+                }
             }
         }
     }
@@ -1307,7 +1327,8 @@ size_t forward_smem_bytes(int M, int coarseN) {
     return sizeof(double) * ((size_t)RING * BW + 32 + (ust > tc ? ust : tc));
 }
 size_t backward_smem_bytes(int M, int coarseN) {
-    return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + coarseN + (coarseN + 1) + 1);
+    return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + coarseN + (coarseN + 1) + 1 +
+                             (3 * (size_t)M + 1) / 2 + 2);
 }
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
@@ -1330,7 +1351,8 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
     pl.ppc = pl.threads / pl.tpp;
     if (pl.ppc < 1) pl.ppc = 1;
     pl.grid = (bv.total_pieces + pl.ppc - 1) / pl.ppc;
-    pl.smem = sizeof(double) * ((size_t)pl.ppc * 60 + (size_t)pl.ppc * 6 * bv.max_faces + (size_t)pl.threads * 20);
+    pl.smem = sizeof(double) * ((size_t)pl.ppc * 60 + (size_t)pl.ppc * 6 * bv.max_faces + (size_t)pl.threads * 20) +
+              16 * (size_t)pl.ppc * bv.max_faces + sizeof(double) * pl.ppc;
     return pl;
 }
 

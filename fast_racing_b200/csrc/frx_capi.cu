@@ -290,12 +290,23 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     UP(wv_cnt, wp_vert_cnt);
     UP(wxi, wp_xi_off);
     UP(faces, faces);
+    {   // single-precision copy for K2's prefilter: skip a face only when  n.pos + slack < d_lo  proves it inactive in fp64
+        std::vector<float> ff(4 * (faces.size() / 6));
+        for (size_t k = 0; k < faces.size() / 6; k++) {
+            const double* f = &faces[6 * k];
+            const double d = f[0] * f[3] + f[1] * f[4] + f[2] * f[5];
+            ff[4 * k + 0] = (float)f[0], ff[4 * k + 1] = (float)f[1], ff[4 * k + 2] = (float)f[2];
+            ff[4 * k + 3] = (float)(d - 1.0e-6 * std::fabs(d) - 1.0e-6);  // rounded down beyond any fp32 error of the test
+        }
+        UP(ff, faces_f32);
+    }
     UP(verts, verts);
 #undef UP
 #define SC(n, field)                                                \
     if ((e = b->scratch((size_t)(n), &bv.field)) != cudaSuccess) return fail(e, "alloc " #field)
     SC(TP, T);
     SC(3 * (size_t)TP, q);
+    SC(4 * (size_t)TP, wpw);
     SC(18 * (size_t)TP, c);
     SC(96 * (size_t)TP, lu);
     SC(18 * (size_t)TP, gdC);
