@@ -319,10 +319,10 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         traffic, traffic_src = None, None
         try:  # dram__bytes_read+write of the penalty kernel per launch, from the committed `ncu --set full` capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_dram_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_dram_traffic.json")))
             if (B, M, S, F) == (1024, 64, 33, 12):
                 traffic = tj["kernels"]["penalty_kernel"]["traffic_bytes"]
-                traffic_src = "profiles/r01b_dram_traffic.json (ncu --set full, same workload)"
+                traffic_src = "profiles/r01c_dram_traffic.json (ncu --set full, same workload)"
         except Exception:
             pass
         pen_s = kms[1] * 1e-3
