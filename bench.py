@@ -301,7 +301,15 @@ def main():
                   "device_ms": r["device_ms"], "ticks": int(r["ticks"]),
                   "iterations_mean": float(r["iterations"].mean()), "evaluations_mean": float(r["evaluations"].mean()),
                   "status_ok_frac": float((r["status"] >= 0).mean()), "argmin": {"cost": best[0], "global_index": best[1]},
-                  "nccl_gather_ms": gather_ms}
+                  "nccl_gather_ms": gather_ms,
+                  # lockstep occupancy: share of (trajectory, tick) slots that still evaluated
+                  "active_slot_frac": float(r["evaluations"].mean()) / max(int(r["ticks"]), 1)}
+        uk = r["update_kernel"]
+        if uk["sampled_launches"] > 0 and uk["device_ms"] > 0:
+            # the HBM-streaming kernel of the path: history bytes of the sampled launches / their device time
+            solves["update_kernel"] = {"sampled_launches": uk["sampled_launches"], "mean_us": 1e3 * uk["device_ms"] / uk["sampled_launches"],
+                                       "history_GB": uk["history_bytes"] / 1e9,
+                                       "achieved_GBps": uk["history_bytes"] / (uk["device_ms"] * 1e-3) / 1e9}
         sbatch.close()
 
     if rank == 0:

@@ -156,6 +156,8 @@ def load_library():
         "frx_host_model": (ci, [P(FrxProblem), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(ci), P(cd)]),
         "frx_host_vpolys": (ci, [P(FrxProblem), P(ci), P(cd)]),
         "frx_batch_solver_ticks": (ci, [vp]),
+        "frx_batch_solver_update_stats": (ci, [vp, P(cd)]),
+        "frx_batch_solver_direction_check": (ci, [vp, P(cd)]),
         "frx_batch_profile_eval": (ci, [vp, vp, vp, vp, vp, ci, P(cd)]),
         "frx_batch_penalty_launch": (ci, [vp, P(C.c_longlong)]),
         "frx_measure_fp64_tflops": (cd, []),
@@ -352,6 +354,12 @@ class Batch:
                                            _ip(r["evaluations"]), _dp(r["x"])), "frx_batch_optimize")
         r["device_ms"] = self.last_ms()
         r["ticks"] = self.lib.frx_batch_solver_ticks(self.h)
+        st = np.zeros(3)
+        self.lib.frx_batch_solver_update_stats(self.h, _dp(st))
+        chk = C.c_double(-1.0)
+        self.lib.frx_batch_solver_direction_check(self.h, C.byref(chk))
+        r["direction_check"] = chk.value
+        r["update_kernel"] = {"sampled_launches": int(st[2]), "device_ms": float(st[0]), "history_bytes": float(st[1])}
         return r
 
     def argmin(self):

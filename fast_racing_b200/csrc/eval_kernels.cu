@@ -98,7 +98,37 @@ __device__ long long g_phase_clk[96];
         if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0)                                       \
             g_phase_clk[(kernel)*32 + (threadIdx.x >> 5) * 16 + (mark)] = clock64();                      \
     } while (0)
+#define PHASE_ACC_DECL long long acc_t0_ = clock64(), acc_work_ = 0, acc_wait_ = 0
+#define PHASE_ACC_WORK()                   \
+    do {                                   \
+        const long long n_ = clock64();    \
+        acc_work_ += n_ - acc_t0_;         \
+        acc_t0_ = n_;                      \
+    } while (0)
+#define PHASE_ACC_WAIT()                   \
+    do {                                   \
+        const long long n_ = clock64();    \
+        acc_wait_ += n_ - acc_t0_;         \
+        acc_t0_ = n_;                      \
+    } while (0)
+#define PHASE_ACC_STORE(kernel)                                                       \
+    do {                                                                              \
+        if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0) {                 \
+            g_phase_clk[(kernel)*32 + (threadIdx.x >> 5) * 16 + 8] = acc_work_;       \
+            g_phase_clk[(kernel)*32 + (threadIdx.x >> 5) * 16 + 9] = acc_wait_;       \
+        }                                                                             \
+    } while (0)
 #else
+#define PHASE_ACC_DECL
+#define PHASE_ACC_WORK() \
+    do {                 \
+    } while (0)
+#define PHASE_ACC_WAIT() \
+    do {                 \
+    } while (0)
+#define PHASE_ACC_STORE(kernel) \
+    do {                        \
+    } while (0)
 #define PHASE_MARK(kernel, mark) \
     do {                         \
     } while (0)
@@ -306,6 +336,97 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 
     PHASE_MARK(0, 2);
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
+#ifndef FRX_EXACT
+    if (warp == 0) {
+        // TWO pivots (k, k+1) per trip: every lane recomputes the update of row k+1 by pivot k for the columns it needs
+        // (and 1/u_{k+1,k+1}), so the pair costs one shared-memory round trip instead of two.  The arithmetic per element is
+        // exactly the sequential one: a_ij -= l_ik u_kj, then a_ij -= l_i,k+1 u_k+1,j.
+        // Lane (r, cg): row i = k+2+r, columns k+2+cg and k+5+cg, right-hand side cg.  Slot of column c in row i: c - i + 6.
+        const int r = lane / 3, cg = lane - 3 * r;
+        constexpr unsigned RB = RING * BW * 8;  // ring size in bytes (power of two)
+        char* const rb = reinterpret_cast<char*>(ring);
+        const bool act = lane < 18;
+        unsigned ok = 0;  // byte offset of pivot row k
+        PHASE_ACC_DECL;
+#ifdef FRX_PHASE_CLK
+        long long pc_[4] = {0, 0, 0, 0}, c0_ = clock64();
+#endif
+        for (int j = 0; j < M; j++) {
+#ifdef FRX_PHASE_CLK
+            c0_ = clock64();
+#endif
+#pragma unroll 1
+            for (int pr = 0; pr < 3; pr++) {
+                if (act) {
+                    const double* R0 = reinterpret_cast<const double*>(rb + ok);
+                    double* R1 = reinterpret_cast<double*>(rb + ((ok + BW * 8) & (RB - 1)));
+                    double* Rw = reinterpret_cast<double*>(rb + ((ok + (2 + r) * BW * 8) & (RB - 1)));
+                    const double rcp0 = R0[6], u01 = R0[7], u0a = R0[8 + cg], u0b = (cg < 2) ? R0[11 + cg] : 0.0, y0 = R0[13 + cg];
+                    const double a10 = R1[5], a11 = R1[6], a1a = R1[7 + cg], a1b = R1[10 + cg], y1r = R1[13 + cg];
+                    const double ai0 = (r < 5) ? Rw[4 - r] : 0.0, ai1 = Rw[5 - r];
+                    const double ea = Rw[6 + cg - r], eb = Rw[9 + cg - r], ey = Rw[13 + cg];
+                    __syncwarp(0x3ffffu);  // every lane holds its operands: the stores below may overwrite them
+#ifdef FRX_PHASE_CLK
+                    const long long c1_ = clock64();
+                    pc_[0] += (c1_ - c0_) + (long long)(ai0 * 0.0);  // operand use pins the loads before this mark
+#endif
+                    // row k+1 by pivot k
+                    const double l10 = a10 * rcp0;  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
+                    const double u11 = a11 - l10 * u01;
+                    const double rcp1 = fast_rcp(u11);
+                    const double u1a = a1a - l10 * u0a, u1b = a1b - l10 * u0b, y1 = y1r - l10 * y0;
+                    // row i by pivots k and k+1
+                    const double li0 = ai0 * rcp0;
+                    const double ti1 = ai1 - li0 * u01;
+                    const double li1 = ti1 * rcp1;
+#ifdef FRX_PHASE_CLK
+                    const long long c2_ = clock64() + (long long)(rcp1 * 0.0);
+                    pc_[1] += c2_ - c1_;
+#endif
+                    const double va = (ea - li0 * u0a) - li1 * u1a;
+                    const double vb = (eb - li0 * u0b) - li1 * u1b;
+                    const double vy = (ey - li0 * y0) - li1 * y1;
+#ifdef FRX_PHASE_CLK
+                    const long long c3_ = clock64() + (long long)(va * 0.0);
+                    pc_[2] += c3_ - c2_;
+#endif
+                    // Lane 0 (r = 0, cg = 0) owns the next pivot u = va and stores 1/u.  With w = ea - li0 u0a:
+                    //   u = w - (ti1/u11) u1a = (w u11 - ti1 u1a) / u11   =>   1/u = u11 / (w u11 - ti1 u1a),
+                    // whose reciprocal does not wait for 1/u11 (the two reciprocals of a pair run concurrently).
+                    const double rnx = u11 * fast_rcp((ea - li0 * u0a) * u11 - ti1 * u1a);
+                    Rw[6 + cg - r] = (lane == 0) ? rnx : va;
+                    Rw[9 + cg - r] = vb;
+                    Rw[13 + cg] = vy;
+                    if (cg == 0) {
+                        if (r < 5) Rw[4 - r] = li0;
+                        Rw[5 - r] = li1;
+                    }
+                    if (r == 0) {  // the finished row k+1
+                        R1[7 + cg] = u1a, R1[10 + cg] = u1b, R1[13 + cg] = y1;
+                        if (cg == 0) R1[5] = l10, R1[6] = rcp1;
+                    }
+                }
+                ok = (ok + 2 * BW * 8) & (RB - 1);
+                __syncwarp();
+#ifdef FRX_PHASE_CLK
+                {
+                    const long long c4_ = clock64();
+                    pc_[3] += c4_ - c0_;
+                    c0_ = c4_;
+                }
+#endif
+            }
+            PHASE_ACC_WORK();
+            cta_bar64();
+            PHASE_ACC_WAIT();
+        }
+        PHASE_ACC_STORE(0);
+#ifdef FRX_PHASE_CLK
+        if (blockIdx.x == gridDim.x / 2 && lane == 0)
+            for (int q = 0; q < 4; q++) g_phase_clk[10 + q] = pc_[q];
+#endif
+    } else {
+#else
     if (warp == 0) {
         const int r = lane / 3, cg = lane - 3 * r;
         constexpr unsigned RB = RING * BW * 8;  // ring size in bytes (power of two)
@@ -352,14 +473,74 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             cta_bar64();
         }
     } else {
-        double Tn = loadT(2), qn = loadq(2);  // operands of the fill of phase 0
+#endif
+        // The feeder's per-phase work is straight-line code on per-lane constants (K1 is issue-bound with seven CTAs per SM):
+        //   fill     slot e = lane + 32 t (t < 3) of the 6 x 16 junction block holds  fc[t] * T^fp[t]  (0 for non-entries),
+        //            except the waypoint row's right-hand side (row 2, columns 13..15 = lanes 13..15 at t = 1);
+        //   retire   48 sixteen-byte chunks of factors to global, and UST compact entries per row for the back substitution.
+        double fc[3];
+        int fp[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int e = lane + 32 * t;
+            fc[t] = 0.0, fp[t] = 0;
+            for (int q = 0; q < 31; q++)
+                if (JR[q] * BW + JS[q] == e) fc[t] = JC[q], fp[t] = JP[q];
+        }
+        const int ue1 = lane + 32;
+        const int ur0 = lane / UST, uq0 = lane - UST * ur0, ur1 = ue1 / UST, uq1 = ue1 - UST * ur1;
+        const bool u1on = ue1 < 6 * UST;
+        auto loadq13 = [&](int g) { return (lane >= 13 && lane < 16 && g >= 0 && g < M - 1) ? stage[4 * g + 1 + (lane - 13)] : 0.0; };
+        double Tn = loadT(2), qn = loadq13(2);  // operands of the fill of phase 0
+        PHASE_ACC_DECL;
         for (int j = 0; j < M; j++) {
             const double Tc_ = Tn, qc_ = qn;
-            Tn = loadT(j + 3), qn = loadq(j + 3);  // prefetch for the next phase (latency hidden behind this phase)
-            fill_block(ring, bv, b, M, j + 2, lane, fl, Tc_, qc_);
-            if (j >= 1) retire_rows(ring, lug, ust, 6 * (j - 1), 6, lane);
+            Tn = loadT(j + 3), qn = loadq13(j + 3);  // prefetch for the next phase
+            const int g = j + 2;
+            if (g < M - 1) {  // junction block g: rows 6g+3 .. 6g+8
+                const int row0 = 6 * g + 3;
+                const double T1 = Tc_, T2 = T1 * T1, T3 = T2 * T1, T4 = T2 * T2, T5 = T4 * T1;
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int e = lane + 32 * t;
+                    double v = (fc[t] != 0.0) ? fc[t] * pick_pow(fp[t], T1, T2, T3, T4, T5) : 0.0;  // structural zeros stay exact
+                    if (t == 1 && lane >= 13 && lane < 16) v = qc_;  // waypoint row 6g+5, right-hand side
+                    ring[((row0 + (e >> 4)) & (RING - 1)) * BW + (e & 15)] = v;
+                }
+            } else {
+                fill_block(ring, bv, b, M, g, lane, fl, Tc_, 0.0);  // tail rows / zero rows / nothing: once each
+            }
+            if (j >= 1) {
+                const int row0 = 6 * (j - 1);
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const int c = lane + 32 * t;  // 16-byte chunk of the 6 x 16 block
+                    if (c < 48)
+                        *reinterpret_cast<double2*>(lug + (size_t)row0 * BW + 2 * c) =
+                            *reinterpret_cast<const double2*>(ring + ((row0 + (c >> 3)) & (RING - 1)) * BW + 2 * (c & 7));
+                }
+                {
+                    const double* rw = ring + ((row0 + ur0) & (RING - 1)) * BW;
+#ifdef FRX_EXACT
+                    ust[(size_t)(row0 + ur0) * UST + uq0] = rw[6 + uq0];
+#else
+                    ust[(size_t)(row0 + ur0) * UST + uq0] = rw[7 + uq0] * rw[6];
+#endif
+                }
+                if (u1on) {
+                    const double* rw = ring + ((row0 + ur1) & (RING - 1)) * BW;
+#ifdef FRX_EXACT
+                    ust[(size_t)(row0 + ur1) * UST + uq1] = rw[6 + uq1];
+#else
+                    ust[(size_t)(row0 + ur1) * UST + uq1] = rw[7 + uq1] * rw[6];
+#endif
+                }
+            }
+            PHASE_ACC_WORK();
             cta_bar64();
+            PHASE_ACC_WAIT();
         }
+        PHASE_ACC_STORE(0);
     }
     PHASE_MARK(0, 3);
     // ---- retire the last six rows ----

@@ -484,6 +484,11 @@ int frx_debug_phase_clocks(long long* out96) {
     CK(frx_fast::fetch_phase_clocks(out96));
     return FRX_OK;
 }
+int frx_debug_update_clocks(long long* out16, int reset) {
+    if (!out16) return FRX_ERR_INVALID_ARG;
+    CK(frx_fast::fetch_update_clocks(out16, reset));
+    return FRX_OK;
+}
 // Launch geometry of the penalty kernel: out[6] = {samples/thread, threads/piece, pieces/CTA, CTA threads, grid, smem bytes}
 int frx_batch_penalty_launch(const frx_batch* b, long long* out) {
     if (!b || !out) return FRX_ERR_INVALID_ARG;
@@ -590,6 +595,7 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     io.x0_host = x0.data();
     io.rel_tol = rel_tol;
     io.stream = b->stream;
+    if (const char* e = getenv("FRX_SOLVER_MAX_TICKS")) io.max_ticks = atoi(e) > 0 ? atoi(e) : io.max_ticks;  // tests: truncated runs
     auto eval = [b](const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
         return b->eval_on(x_dev, cost_dev, grad_dev, st);
     };
@@ -647,6 +653,28 @@ int frx_batch_solver_ticks(const frx_batch* b) {
     if (!b) return 0;
     if (b->last_solver_exact) return b->solver_x ? frx_exact::solver_ticks(b->solver_x) : 0;
     return b->solver ? frx_fast::solver_ticks(b->solver) : 0;
+}
+
+// Sampled lbfgs_update_kernel launches of the last frx_batch_optimize: out[3] = {device ms, algorithmic history bytes streamed, samples}
+int frx_batch_solver_update_stats(const frx_batch* b, double* out) {
+    if (!b || !out) return FRX_ERR_INVALID_ARG;
+    int n = 0;
+    out[0] = out[1] = out[2] = 0.0;
+    if (b->last_solver_exact) {
+        if (b->solver_x) frx_exact::solver_update_stats(b->solver_x, &out[0], &out[1], &n);
+    } else if (b->solver)
+        frx_fast::solver_update_stats(b->solver, &out[0], &out[1], &n);
+    out[2] = n;
+    return FRX_OK;
+}
+
+// FRX_LBFGS_CHECK=1 (set before the first optimize of the handle): largest relative deviation between the vector-free
+// direction and the two-loop recursion over the last solve; -1 when the check was off.
+int frx_batch_solver_direction_check(const frx_batch* b, double* max_rel) {
+    if (!b || !max_rel) return FRX_ERR_INVALID_ARG;
+    *max_rel = -1.0;
+    if (!b->last_solver_exact && b->solver) return frx_fast::solver_direction_check(b->solver, max_rel);
+    return FRX_OK;
 }
 
 int frx_batch_argmin(frx_batch* b, int* best_traj, double* best_cost) {

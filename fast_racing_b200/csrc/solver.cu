@@ -106,9 +106,107 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Gram matrices per trajectory: SY[i][j] = s_i.y_j, SYT = SY^T, YY[i][j] = y_i.y_j (m x m each).
 // Requires m <= 128 and UPD_THREADS == 256.
 // ---------------------------------------------------------------------------------------------
+// Phase clocks of the update kernel (debug builds: FRX_NVCC_EXTRA=-DFRX_PHASE_CLK): thread 0 of CTA 0 accumulates the
+// clock64() differences between marks over all launches; scripts/phase_clocks_solver.py prints them.
+__device__ long long g_upd_clk[16];
+#ifdef FRX_PHASE_CLK
+#define UPD_MARK(i)                                   \
+    do {                                              \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {    \
+            const long long now_ = clock64();         \
+            g_upd_clk[i] += now_ - upd_t0_;           \
+            upd_t0_ = now_;                           \
+        }                                             \
+    } while (0)
+#define UPD_MARK_DECL long long upd_t0_ = clock64()
+#define UPD_MARK_ARG , long long& upd_t0_
+#define UPD_MARK_PASS , upd_t0_
+#else
+#define UPD_MARK(i) \
+    do {            \
+    } while (0)
+#define UPD_MARK_DECL
+#define UPD_MARK_ARG
+#define UPD_MARK_PASS
+#endif
+
+// One of the two L-BFGS recursions, expressed on a Gram matrix Mx (row = the pair being solved, column = an already solved
+// pair) as a unit-triangular solve over the pairs in age order, blocked by 16, RIGHT-LOOKING:
+//   tacc[o]  running value of (vector . current direction) for the pair of age o (initialised by the caller),
+//   step     val = tacc * (1 / ys);  coefficient = -val (LOOP 1: -alpha) or alpha - val (LOOP 2: alpha - beta),
+//   update   every later pair:  tacc[o2] += coefficient * Mx[slot(o2)][slot(o)].
+// Per block: the 16 x 16 diagonal part is sequential on 16 lanes (each lane owns one row in registers; one shuffle
+// broadcast + one FMA per step), while the panel below it - whose loads do not depend on the new coefficients - is
+// fetched BEFORE the sequential part and applied after it by the whole CTA; the next diagonal block is fetched in the
+// same shadow.  Deterministic (fixed order).  Requires UPD_THREADS == 256, bound <= 128.
+template <int LOOP>
+__device__ __forceinline__ void blocked_recursion(const double* __restrict__ Mx, int m, int bound, double* tacc, const double* rys,
+                                                  double* al, double* coef_out, double (*dblk)[16][17], double* cbk, const int* slot) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rr = tid >> 4, cc = tid & 15;  // 16 rows x 16 columns
+    if (rr < min(16, bound) && cc < min(16, bound)) dblk[0][rr][cc] = Mx[(size_t)slot[rr] * m + slot[cc]];
+    __syncthreads();
+    int cur = 0;
+    for (int ob = 0; ob < bound; ob += 16, cur ^= 1) {
+        const int nb = min(16, bound - ob);
+        double pv[7];
+#pragma unroll
+        for (int t = 0; t < 7; t++) {
+            const int o2 = ob + 16 + rr + 16 * t;
+            pv[t] = (o2 < bound && cc < nb) ? Mx[(size_t)slot[o2] * m + slot[ob + cc]] : 0.0;
+        }
+        double nd = 0.0;
+        {
+            const int r2 = ob + 16 + rr, c2 = ob + 16 + cc;
+            if (r2 < bound && c2 < bound) nd = Mx[(size_t)slot[r2] * m + slot[c2]];
+        }
+        if (warp == 0) {
+            const int r = lane & 15;  // both half-warps run the same recursion (width-16 shuffles); lanes < 16 publish
+            const bool on = r < nb;
+            double a = on ? tacc[ob + r] : 0.0;
+            double drow[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) drow[c] = dblk[cur][r][c];
+            const int js = on ? slot[ob + r] : 0;
+            const double ry = on ? rys[js] : 0.0;
+            const double alr = (LOOP == 2 && on) ? al[js] : 0.0;
+            double mycoef = 0.0, myval = 0.0;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                if (c < nb) {  // uniform
+                    const double val = a * ry;
+                    const double cf = (LOOP == 1) ? -val : (alr - val);
+                    const double cfb = __shfl_sync(0xffffffffu, cf, c, 16);
+                    if (r == c) mycoef = cfb, myval = val;
+                    if (r > c) a += cfb * drow[c];
+                }
+            }
+            if (lane < nb) {
+                cbk[lane] = mycoef;
+                coef_out[js] = mycoef;
+                if (LOOP == 1) al[js] = myval;
+            }
+        }
+        __syncthreads();
+        {
+            const double ck = cc < nb ? cbk[cc] : 0.0;
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                const int o2 = ob + 16 + rr + 16 * t;
+                double v = pv[t] * ck;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+                if (cc == 0 && o2 < bound) tacc[o2] += v;
+            }
+            dblk[cur ^ 1][rr][cc] = nd;
+        }
+        __syncthreads();
+    }
+}
+
 __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m, int end, int bound,
                                       const double* __restrict__ g, double* __restrict__ d, const double* __restrict__ S,
-                                      const double* __restrict__ Y, double* ysv) {
+                                      const double* __restrict__ Y, double* ysv UPD_MARK_ARG) {
     __shared__ double sg[128], yg[128], cb[128], ca[128], tv[128], al[128];
     __shared__ double sh_gamma;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -159,102 +257,59 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
         }
     }
     __syncthreads();
-    // ---- loop 1 (newest -> oldest): alpha_j = (s_j . q) / ys_j,  q -= alpha_j y_j ----
-    // Blocked by 16 history pairs: the contribution of all EARLIER blocks to the 16 rows of a block is a dense
-    // 16 x (#earlier) mat-vec done by the whole CTA (16 threads per row, coalesced row reads, one global round
-    // trip per block); only the 16 x 16 diagonal block is sequential, from shared memory, on 16 lanes.
-    // Age order: o = 0 is the newest pair, slot(o) = (end - o) mod m.
-    __shared__ double tpart[16];
-    __shared__ double dblk[16][17];
-    const int rr = tid >> 4, cc = tid & 15;  // 16 rows x 16 threads
-    for (int l = tid; l < 128; l += UPD_THREADS) cb[l] = 0.0, ca[l] = 0.0;
-    __syncthreads();
-    for (int ob = 0; ob < bound; ob += 16) {
-        const int nb = min(16, bound - ob);
-        {
-            double t = 0.0;
-            if (rr < nb) {
-                const int j = (end - (ob + rr) + 2 * m) % m;
-                const double* row = SY + (size_t)j * m;
-                for (int o2 = cc; o2 < ob; o2 += 16) {
-                    const int l = (end - o2 + 2 * m) % m;
-                    t += cb[l] * row[l];
-                }
-                if (cc < nb) dblk[rr][cc] = row[(end - (ob + cc) + 2 * m) % m];
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 16);
-            if (cc == 0) tpart[rr] = t;
+    UPD_MARK(4);
+    // ---- the two recursions on the Gram matrices (see blocked_recursion) ----
+    __shared__ double tacc[128], rys[128], cbk[16];
+    __shared__ double dblk[2][16][17];
+    __shared__ int slot[128];
+    for (int l = tid; l < 128; l += UPD_THREADS) {
+        cb[l] = 0.0, ca[l] = 0.0;
+        if (l < bound) {
+            rys[l] = 1.0 / ysv[l];
+            slot[l] = (end - l + 2 * m) % m;  // loop 1: age o = 0 is the NEWEST pair
         }
-        __syncthreads();
-        if (warp == 0) {
-            double bl = 0.0;  // lane c < 16 holds the coefficient of pair ob + c once computed
-            for (int r2 = 0; r2 < nb; r2++) {
-                const int j = (end - (ob + r2) + 2 * m) % m;
-                double v = (lane < r2) ? bl * dblk[r2][lane] : 0.0;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
-                const double alpha = (v + tpart[r2] - sg[j]) / ysv[j];
-                if (lane == r2) {
-                    bl = -alpha;
-                    al[j] = alpha;
-                    cb[j] = -alpha;
-                }
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    for (int o = tid; o < bound; o += UPD_THREADS) tacc[o] = -sg[slot[o]];  // d = -g: s_j . d starts at -(s_j . g)
+    __syncthreads();
+    // loop 1 (newest -> oldest): alpha_j = (s_j . q) / ys_j, q -= alpha_j y_j  ->  cb_j = -alpha_j
+    blocked_recursion<1>(SY, m, bound, tacc, rys, al, cb, dblk, cbk, slot);
+    UPD_MARK(5);
     if (tid == 0) sh_gamma = ysv[end] / YY[(size_t)end * m + end];  // ys / yy of the newest pair
     __syncthreads();
     const double gamma = sh_gamma;
     for (int l = tid; l < 128; l += UPD_THREADS) cb[l] *= gamma;
     __syncthreads();
     const double dg = -gamma;  // coefficient of g
-    // t_j = dg * (y_j . g) + sum_l b_l (y_j . y_l): independent of the second recursion
-    if (tid < bound) {
-        double t = 0.0;
-#pragma unroll 4
-        for (int l = 0; l < bound; l++) t += cb[l] * YY[(size_t)l * m + tid];
-        tv[tid] = dg * yg[tid] + t;
+    // t_j = dg * (y_j . g) + sum_l b_l (y_j . y_l): independent of the second recursion.  Two threads per j, four
+    // independent partial sums each (the loads of a trip are in flight together).
+    {
+        const int j = tid & 127, half = tid >> 7;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        if (j < bound) {
+            const int l0 = half * 64, l1 = min(bound, l0 + 64);
+            int l = l0;
+            for (; l + 4 <= l1; l += 4) {
+                t0 += cb[l] * YY[(size_t)l * m + j];
+                t1 += cb[l + 1] * YY[(size_t)(l + 1) * m + j];
+                t2 += cb[l + 2] * YY[(size_t)(l + 2) * m + j];
+                t3 += cb[l + 3] * YY[(size_t)(l + 3) * m + j];
+            }
+            for (; l < l1; l++) t0 += cb[l] * YY[(size_t)l * m + j];
+        }
+        if (half == 1 && j < bound) tv[j] = (t0 + t1) + (t2 + t3);
+        __syncthreads();
+        if (half == 0 && j < bound) tv[j] = dg * yg[j] + (((t0 + t1) + (t2 + t3)) + tv[j]);
     }
     __syncthreads();
-    // ---- loop 2 (oldest -> newest): beta = (y_j . r) / ys_j,  r += (alpha_j - beta) s_j ----
-    // Same blocking; age order now o = 0 is the OLDEST pair: slot(o) = (end - (bound-1) + o) mod m; the row of
-    // pair j is SYT[j][l] = s_l . y_j.
-    for (int ob = 0; ob < bound; ob += 16) {
-        const int nb = min(16, bound - ob);
-        {
-            double t = 0.0;
-            if (rr < nb) {
-                const int j = (end - (bound - 1) + (ob + rr) + 2 * m) % m;
-                const double* row = SYT + (size_t)j * m;
-                for (int o2 = cc; o2 < ob; o2 += 16) {
-                    const int l = (end - (bound - 1) + o2 + 2 * m) % m;
-                    t += ca[l] * row[l];
-                }
-                if (cc < nb) dblk[rr][cc] = row[(end - (bound - 1) + (ob + cc) + 2 * m) % m];
-            }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o, 16);
-            if (cc == 0) tpart[rr] = t;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double al2 = 0.0;
-            for (int r2 = 0; r2 < nb; r2++) {
-                const int j = (end - (bound - 1) + (ob + r2) + 2 * m) % m;
-                double v = (lane < r2) ? al2 * dblk[r2][lane] : 0.0;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
-                const double beta = (tv[j] + tpart[r2] + v) / ysv[j];
-                if (lane == r2) {
-                    al2 = al[j] - beta;
-                    ca[j] = al2;
-                }
-            }
-        }
-        __syncthreads();
-    }
+    UPD_MARK(6);
+    // loop 2 (oldest -> newest): beta = (y_j . r) / ys_j, r += (alpha_j - beta) s_j  ->  ca_j = alpha_j - beta_j
+    for (int o = tid; o < bound; o += UPD_THREADS) slot[o] = (end - (bound - 1) + o + 2 * m) % m;  // age o = 0 is the OLDEST pair
+    __syncthreads();
+    for (int o = tid; o < bound; o += UPD_THREADS) tacc[o] = tv[slot[o]];
+    __syncthreads();
+    blocked_recursion<2>(SYT, m, bound, tacc, rys, al, ca, dblk, cbk, slot);
+    UPD_MARK(7);
     // ---- pass 2: d = dg*g + sum_l ca_l s_l + cb_l y_l ----
     for (int base = 0; base < n; base += UPD_THREADS * 4) {
         double acc[4];
@@ -278,6 +333,36 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
             if (idx[e] < n) d[idx[e]] = acc[e];
     }
     __syncthreads();
+    UPD_MARK(8);
+}
+
+// The sequential two-loop recursion in the reference's order (lbfgs.hpp:1359-1411) on dv, which holds -g on entry.
+__device__ void direction_two_loop(double* dv, int n, int m, int end1, int bound, const double* S, const double* Y, const double* ysv,
+                                   double* alv, double ys, double yy, double* red) {
+    const int tid = threadIdx.x;
+    int j = end1;
+    for (int it = 0; it < bound; it++) {
+        j = (j + m - 1) % m;
+        const double* sj = S + (size_t)j * n;
+        const double* yj = Y + (size_t)j * n;
+        const double a = block_dot(sj, dv, n, red) / ysv[j];
+        if (tid == 0) alv[j] = a;
+        const double c = -a;
+        for (int i = tid; i < n; i += UPD_THREADS) dv[i] += c * yj[i];
+    }
+    {
+        const double sc = ys / yy;
+        for (int i = tid; i < n; i += UPD_THREADS) dv[i] *= sc;
+    }
+    __syncthreads();  // alv[] written by thread 0 above
+    for (int it = 0; it < bound; it++) {
+        const double* sj = S + (size_t)j * n;
+        const double* yj = Y + (size_t)j * n;
+        const double beta = block_dot(yj, dv, n, red) / ysv[j];
+        const double c = alv[j] - beta;
+        for (int i = tid; i < n; i += UPD_THREADS) dv[i] += c * sj[i];
+        j = (j + 1) % m;
+    }
 }
 
 // Outcome codes shared through smem
@@ -306,6 +391,7 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
     const LbfgsConfig& P = sv.cfg;
     const double f = sv.cost[b];
     const int phase = st->phase;
+    UPD_MARK_DECL;
 
     bool start_iter = false;  // uniform across the CTA
 
@@ -335,6 +421,7 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
         if (sh_act == ACT_NEXT_ITER) start_iter = true;
     } else {
         const double dg = block_dot(g, d, n, red);
+        UPD_MARK(0);
         if (tid == 0) {
             st->n_evals++;
             int oc = (phase == PH_MT) ? st->ls.mt_feed(f, dg, P) : st->ls.bt_feed(f, dg, P);
@@ -367,8 +454,10 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
             }
         } else if (sh_act == ACT_NEXT_ITER) {
             // ---- lbfgs.hpp:1294-1416 ----
+            UPD_MARK(1);
             double xx, gg;
             block_dot2(x, x, g, g, n, red, xx, gg);
+            UPD_MARK(2);
             if (tid == 0) {
                 double xnorm = sqrt(xx);
                 const double gnorm = sqrt(gg);
@@ -417,34 +506,34 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
                     st->end = end1;
                 }
                 __syncthreads();
+                UPD_MARK(3);
+                // measurement only: the direction update streams the history twice, (4 bound + 4) n doubles
+                if (sv.count_bytes && tid == 0) atomicAdd(sv.hist_bytes, 8ull * (4ull * bound + 4ull) * (unsigned long long)n);
                 if (sv.vector_free) {
-                    direction_vector_free(sv, b, n, m, end, bound, g, d, S, Y, ysv);
+                    direction_vector_free(sv, b, n, m, end, bound, g, d, S, Y, ysv UPD_MARK_PASS);
+                    if (sv.check_dir) {  // self-check (FRX_LBFGS_CHECK=1): the two-loop recursion on a scratch vector
+                        double* dc = sv.dchk + xo;
+                        for (int i = tid; i < n; i += UPD_THREADS) dc[i] = -g[i];
+                        __syncthreads();
+                        direction_two_loop(dc, n, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
+                        double emax = 0.0, dmax = 0.0;
+                        for (int i = tid; i < n; i += UPD_THREADS) emax = fmax(emax, fabs(d[i] - dc[i])), dmax = fmax(dmax, fabs(dc[i]));
+                        __shared__ double chk[2][UPD_THREADS / 32];
+                        for (int o = 16; o > 0; o >>= 1)
+                            emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o)), dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+                        if ((tid & 31) == 0) chk[0][tid >> 5] = emax, chk[1][tid >> 5] = dmax;
+                        __syncthreads();
+                        if (tid == 0) {
+                            for (int w = 1; w < UPD_THREADS / 32; w++) emax = fmax(emax, chk[0][w]), dmax = fmax(dmax, chk[1][w]);
+                            const double rel = dmax > 0.0 ? emax / dmax : 0.0;
+                            atomicMax(sv.dir_err_bits, (unsigned long long)__double_as_longlong(rel));  // rel >= 0: bit order = value order
+                        }
+                        __syncthreads();
+                    }
                     if (tid == 0) st->step = 1.0;
                     start_iter = true;
                 } else {
-                int j = end1;
-                for (int it = 0; it < bound; it++) {
-                    j = (j + m - 1) % m;
-                    const double* sj = S + (size_t)j * n;
-                    const double* yj = Y + (size_t)j * n;
-                    const double a = block_dot(sj, d, n, red) / ysv[j];
-                    if (tid == 0) alv[j] = a;
-                    const double c = -a;
-                    for (int i = tid; i < n; i += UPD_THREADS) d[i] += c * yj[i];
-                }
-                {
-                    const double sc = ys / yy;
-                    for (int i = tid; i < n; i += UPD_THREADS) d[i] *= sc;
-                }
-                __syncthreads();  // alv[] written by thread 0 above
-                for (int it = 0; it < bound; it++) {
-                    const double* sj = S + (size_t)j * n;
-                    const double* yj = Y + (size_t)j * n;
-                    const double beta = block_dot(yj, d, n, red) / ysv[j];
-                    const double c = alv[j] - beta;
-                    for (int i = tid; i < n; i += UPD_THREADS) d[i] += c * sj[i];
-                    j = (j + 1) % m;
-                }
+                direction_two_loop(d, n, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
                 if (tid == 0) st->step = 1.0;
                 start_iter = true;
                 }
@@ -459,6 +548,7 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
             gp[i] = g[i];
         }
         const double dg0 = block_dot(g, d, n, red);
+        UPD_MARK(9);
         if (tid == 0) {
             st->stepp = st->step;
             st->fp = st->fx;
@@ -494,6 +584,15 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
             atomicSub(sv.n_active, 1);
         }
     }
+    UPD_MARK(10);
+}
+cudaError_t fetch_update_clocks(long long* out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_upd_clk, sizeof(long long) * 16);
+    if (e == cudaSuccess && reset) {
+        long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_upd_clk, z, sizeof(z));
+    }
+    return e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,6 +640,9 @@ struct SolverState {
     double* am_val = nullptr;
     int* pin_int = nullptr;
     double* pin_dbl = nullptr;
+    std::vector<cudaEvent_t> ev;  // pairs around the sampled update launches
+    int n_samples = 0;
+    double upd_ms = 0.0, upd_bytes = 0.0;
 };
 
 template <class T>
@@ -586,7 +688,14 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
          dalloc(s, m * m * bv.B, &sv.SY) == cudaSuccess && dalloc(s, m * m * bv.B, &sv.SYT) == cudaSuccess &&
          dalloc(s, m * m * bv.B, &sv.YY) == cudaSuccess &&
          dalloc(s, (size_t)bv.B, &s->fx_dev) == cudaSuccess && dalloc(s, 1, &s->am_idx) == cudaSuccess &&
-         dalloc(s, 1, &s->am_val) == cudaSuccess;
+         dalloc(s, 1, &s->am_val) == cudaSuccess && dalloc(s, 1, &sv.hist_bytes) == cudaSuccess &&
+         dalloc(s, 1, &sv.dir_err_bits) == cudaSuccess;
+    {
+        const char* e = getenv("FRX_LBFGS_CHECK");  // self-check of the vector-free direction against the two-loop recursion
+        sv.check_dir = (e && e[0] == '1' && sv.vector_free) ? 1 : 0;
+        sv.dchk = nullptr;
+        if (sv.check_dir) ok = ok && dalloc(s, nx, &sv.dchk) == cudaSuccess;
+    }
     ok = ok && cudaMallocHost(&s->pin_int, sizeof(int) * 4) == cudaSuccess &&
          cudaMallocHost(&s->pin_dbl, sizeof(double) * 4) == cudaSuccess;
     if (!ok) {
@@ -601,6 +710,7 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
 void solver_destroy(SolverState* s) {
     if (!s) return;
     for (void* p : s->allocs) cudaFree(p);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     if (s->pin_int) cudaFreeHost(s->pin_int);
     if (s->pin_dbl) cudaFreeHost(s->pin_dbl);
     delete s;
@@ -617,22 +727,61 @@ int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, const EvalFn& 
     SolverView& sv = s->sv;
     solver_bind_active(bv, s, true);
     int ticks = 0, n_active = bv.B;
+    // Measurement: the first update launch of every poll group is bracketed by events and counts the history bytes it
+    // streams (-> achieved HBM bandwidth of the direction update, bench.py "solves.update_kernel").
+    s->n_samples = 0;
+    if (cudaMemsetAsync(sv.hist_bytes, 0, sizeof(unsigned long long), io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+    if (cudaMemsetAsync(sv.dir_err_bits, 0, sizeof(unsigned long long), io.stream) != cudaSuccess) return FRX_ERR_CUDA;
     while (n_active > 0 && ticks < io.max_ticks) {
         for (int t = 0; t < io.poll_every; t++) {
             if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            const bool sample = (t == 0);
+            if (sample) {
+                if ((int)s->ev.size() < 2 * (s->n_samples + 1)) {
+                    cudaEvent_t a, b2;
+                    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b2) != cudaSuccess) return FRX_ERR_CUDA;
+                    s->ev.push_back(a), s->ev.push_back(b2);
+                }
+                cudaEventRecord(s->ev[2 * s->n_samples], io.stream);
+            }
+            sv.count_bytes = sample ? 1 : 0;
             if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            if (sample) cudaEventRecord(s->ev[2 * s->n_samples + 1], io.stream), s->n_samples++;
             ticks++;
         }
         r = solver_poll_active(s, io.stream, &n_active);
         if (r != FRX_OK) return r;
     }
     s->ticks = ticks;
+    {
+        unsigned long long hb = 0;
+        if (cudaMemcpyAsync(&hb, sv.hist_bytes, sizeof(hb), cudaMemcpyDeviceToHost, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+        if (cudaStreamSynchronize(io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+        s->upd_bytes = (double)hb, s->upd_ms = 0.0;
+        for (int i = 0; i < s->n_samples; i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]);
+            s->upd_ms += ms;
+        }
+    }
     // final forward pass at the final iterates of ALL trajectories (CPU.hpp:1258-1262)
     solver_bind_active(bv, s, false);
     if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
     return FRX_OK;
 }
 int solver_ticks(SolverState* s) { return s->ticks; }
+int solver_direction_check(SolverState* s, double* max_rel) {
+    unsigned long long bits = 0;
+    if (cudaMemcpy(&bits, s->sv.dir_err_bits, sizeof(bits), cudaMemcpyDeviceToHost) != cudaSuccess) return FRX_ERR_CUDA;
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    *max_rel = s->sv.check_dir ? v : -1.0;
+    return FRX_OK;
+}
+int solver_update_stats(SolverState* s, double* ms, double* bytes, int* samples) {
+    *ms = s->upd_ms, *bytes = s->upd_bytes, *samples = s->n_samples;
+    return FRX_OK;
+}
 const double* solver_final_cost_dev(SolverState* s) { return s->fx_dev; }
 void solver_bind_active(BatchView& bv, SolverState* s, bool on) { bv.active = on ? s->sv.active : nullptr; }
 

@@ -42,6 +42,11 @@ struct SolverView {
     double *ys, *alpha;            // mem_size per trajectory
     double *SY, *SYT, *YY;         // mem_size^2 per trajectory: Gram matrices of the vector-free direction update
     int vector_free;               // 1: vector-free direction update (default); 0: sequential two-loop in the reference's order
+    unsigned long long* hist_bytes;  // measurement: algorithmic history bytes streamed by the sampled launches (see solver_run)
+    int count_bytes;                 // 1 on sampled launches
+    double* dchk;                    // self-check (FRX_LBFGS_CHECK=1): scratch direction of the two-loop recursion
+    unsigned long long* dir_err_bits;  // max relative deviation |d_vf - d_two_loop|_inf / |d_two_loop|_inf, as double bits
+    int check_dir;
 };
 
 struct SolverIO {
@@ -69,6 +74,10 @@ struct SolverIO {
     const double* solver_final_cost_dev(SolverState* s);                                                                    \
     int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st, int* idx, double* val);               \
     int solver_ticks(SolverState* s);                                                                                       \
+    cudaError_t fetch_update_clocks(long long* out16, int reset);                                                           \
+    /* sampled lbfgs_update_kernel launches of the last run: device ms, algorithmic bytes streamed, number of samples */   \
+    int solver_update_stats(SolverState* s, double* ms, double* bytes, int* samples);                                       \
+    int solver_direction_check(SolverState* s, double* max_rel);                                                            \
     }
 FRX_DECLARE_SOLVER_API(frx_fast)
 FRX_DECLARE_SOLVER_API(frx_exact)

@@ -254,6 +254,19 @@ def test_solver_converged_cost_matches_oracle(oracle_mod):
     batch.close()
 
 
+def test_vector_free_direction_matches_two_loop_recursion(monkeypatch):
+    """The vector-free direction update (Gram-matrix recursions as blocked right-looking solves) against the sequential
+    two-loop recursion of lbfgs.hpp:1359-1411: with FRX_LBFGS_CHECK=1 the update kernel computes BOTH at every iteration
+    of a full solve (history growing through every block size up to the full 128 pairs) and records the largest deviation."""
+    monkeypatch.setenv("FRX_LBFGS_CHECK", "1")
+    probs = synth.make_batch(4, 8, 10, 12, 31)
+    b = api.Batch(probs)
+    r = b.optimize(1e-9)
+    assert (r["iterations"] > 200).any(), r["iterations"]  # the history filled up
+    assert 0.0 <= r["direction_check"] <= 1e-9, r["direction_check"]
+    b.close()
+
+
 def test_solver_reference_tolerance_within_sensitivity_band(oracle_mod):
     """At the reference's own delta = 1e-5 the GPU result lies inside the oracle's ulp-perturbation band."""
     probs = synth.make_batch(60, 4, 8, 12, 16)
