@@ -319,8 +319,9 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
             idx[e] = base + e * UPD_THREADS + tid;
             acc[e] = idx[e] < n ? dg * g[idx[e]] : 0.0;
         }
+        // newest-streamed slots first: pass 1 walked the slots upwards, so the tail of the history is what the L2 still holds
 #pragma unroll 8
-        for (int l = 0; l < bound; l++) {
+        for (int l = bound - 1; l >= 0; l--) {
             const double a = ca[l], bb = cb[l];
             const double* sl = S + (size_t)l * n;
             const double* yl = Y + (size_t)l * n;
