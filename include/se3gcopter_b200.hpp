@@ -22,6 +22,7 @@
 // Batch extension (not in the reference, which optimises one trajectory per call): frx::SE3GCOPTERBatch
 // solves many candidate trajectories at once and returns the arg-min.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <stdexcept>
@@ -38,6 +39,64 @@
 #endif
 
 namespace frx {
+
+namespace detail {
+// Polynomials with coefficients in ASCENDING powers.  real_roots: every real root of p in [lo, hi] (simple roots and roots at
+// the ends; used for the stationary points of |vel|^2 / |acc|^2), by recursion on the derivative - the roots of p' split
+// [lo, hi] into monotone pieces - and bisection to `tol` on each piece with a sign change.  Replaces what the reference gets
+// from root_finder.hpp (closed forms / Sturm sequences / companion eigenvalues, trajectory.hpp:177-273) for these queries.
+inline double poly_val(const std::vector<double>& p, double t) {
+    double v = 0.0;
+    for (int i = (int)p.size() - 1; i >= 0; i--) v = v * t + p[i];
+    return v;
+}
+inline std::vector<double> poly_der(const std::vector<double>& p) {
+    std::vector<double> d;
+    for (size_t i = 1; i < p.size(); i++) d.push_back(p[i] * (double)i);
+    return d;
+}
+inline std::vector<double> poly_sqr_sum3(const std::vector<double> (&a)[3]) {  // sum_d a_d(t)^2
+    std::vector<double> q(2 * a[0].size() - 1, 0.0);
+    for (int d = 0; d < 3; d++)
+        for (size_t i = 0; i < a[d].size(); i++)
+            for (size_t j = 0; j < a[d].size(); j++) q[i + j] += a[d][i] * a[d][j];
+    return q;
+}
+inline void real_roots(std::vector<double> p, double lo, double hi, double tol, std::vector<double>& out) {
+    double scale = 0.0;
+    for (double c : p) scale = std::max(scale, std::fabs(c));
+    while (!p.empty() && std::fabs(p.back()) <= 1e-300 + 1e-15 * scale) p.pop_back();  // drop vanishing leading terms
+    if (p.size() < 2) return;
+    if (p.size() == 2) {
+        const double r = -p[0] / p[1];
+        if (r >= lo && r <= hi) out.push_back(r);
+        return;
+    }
+    std::vector<double> knots{lo};
+    real_roots(poly_der(p), lo, hi, tol, knots);
+    knots.push_back(hi);
+    std::sort(knots.begin(), knots.end());
+    for (size_t i = 0; i + 1 < knots.size(); i++) {
+        double a = knots[i], b = knots[i + 1];
+        double fa = poly_val(p, a), fb = poly_val(p, b);
+        if (fa == 0.0) out.push_back(a);
+        if (i + 2 == knots.size() && fb == 0.0) out.push_back(b);
+        if (fa * fb >= 0.0) continue;  // monotone on (a, b): no interior root without a sign change
+        while (b - a > tol) {
+            const double m = 0.5 * (a + b), fm = poly_val(p, m);
+            if (fm == 0.0) {
+                a = b = m;
+                break;
+            }
+            if ((fm < 0.0) == (fa < 0.0))
+                a = m, fa = fm;
+            else
+                b = m;
+        }
+        out.push_back(0.5 * (a + b));
+    }
+}
+}  // namespace detail
 
 // ---- trajectory containers (trajectory.hpp:43-145, 317-593) -------------------------------------
 class Piece {
@@ -69,8 +128,30 @@ public:
         }
         return n;
     }
+    // trajectory.hpp:177-273: exact maximum of |vel| / |acc| over the piece - the stationary points of the squared norm
+    // (roots of its derivative in [0, T], isolated to FLT_EPSILON * T as the reference) and the two ends.
+    double getMaxVelRate() const { return maxRate(1); }
+    double getMaxAccRate() const { return maxRate(2); }
+    // trajectory.hpp:275-313: true iff the rate stays below the limit on the whole piece
+    bool checkMaxVelRate(double maxVelRate) const { return maxRate(1) < maxVelRate; }
+    bool checkMaxAccRate(double maxAccRate) const { return maxRate(2) < maxAccRate; }
 
 private:
+    double maxRate(int deriv) const {
+        std::vector<double> a[3];
+        for (int d = 0; d < 3; d++)
+            for (int p = deriv; p <= 5; p++) {  // power p of t has column 5 - p
+                double f = 1.0;
+                for (int q = 0; q < deriv; q++) f *= (double)(p - q);
+                a[d].push_back(f * c[3 * (5 - p) + d]);
+            }
+        const std::vector<double> q = detail::poly_sqr_sum3(a);
+        std::vector<double> cand{0.0, duration};
+        detail::real_roots(detail::poly_der(q), 0.0, duration, 1.1920929e-07 * duration, cand);
+        double m = 0.0;
+        for (double t : cand) m = std::max(m, detail::poly_val(q, t));
+        return std::sqrt(std::max(m, 0.0));
+    }
     std::array<double, 3> eval(double t, int deriv) const {
         std::array<double, 3> out{0.0, 0.0, 0.0};
         double tn = 1.0;
@@ -138,23 +219,74 @@ public:
         const double b1 = (y[1] * j[1] + y[2] * j[2]) / thr;
         return {-b1, b0, 0.0};
     }
-    // Sampled maxima of |vel| / |acc| (the reference isolates polynomial roots, trajectory.hpp:177-273 via
-    // root_finder.hpp; dense sampling is used here for the printed report only, MinCoPlan_CPU.cpp:131-132).
-    double getMaxVelRate(int samples_per_piece = 256) const { return maxRate(1, samples_per_piece); }
-    double getMaxAccRate(int samples_per_piece = 256) const { return maxRate(2, samples_per_piece); }
-
-private:
-    double maxRate(int deriv, int n) const {
+    // trajectory.hpp:565-577: body frame for a yaw angle; rotM is 3x3 column-major (columns xB, yB, zB)
+    void getRotation(double t, double yaw, double gAcc, double* rotM) const {
+        auto z = getAcc(t);
+        z[2] += gAcc;
+        const double zn = std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+        for (int d = 0; d < 3; d++) z[d] /= zn;
+        const double hx = std::cos(yaw), hy = std::sin(yaw);
+        double y[3] = {z[1] * 0.0 - z[2] * hy, z[2] * hx - z[0] * 0.0, z[0] * hy - z[1] * hx};  // z x (cos yaw, sin yaw, 0)
+        const double yn = std::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+        for (int d = 0; d < 3; d++) y[d] /= yn;
+        const double x[3] = {y[1] * z[2] - y[2] * z[1], y[2] * z[0] - y[0] * z[2], y[0] * z[1] - y[1] * z[0]};  // y x z
+        for (int d = 0; d < 3; d++) rotM[d] = x[d], rotM[3 + d] = y[d], rotM[6 + d] = z[d];
+    }
+    // trajectory.hpp:517-559: maxima over the pieces (exact per piece, see Piece::getMaxVelRate) and the feasibility checks
+    double getMaxVelRate() const {
         double m = 0.0;
-        for (const auto& p : pieces)
-            for (int k = 0; k <= n; k++) {
-                const double t = p.getDuration() * k / n;
-                const auto v = deriv == 1 ? p.getVel(t) : p.getAcc(t);
-                m = std::max(m, std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
-            }
+        for (const auto& p : pieces) m = std::max(m, p.getMaxVelRate());
         return m;
     }
+    double getMaxAccRate() const {
+        double m = 0.0;
+        for (const auto& p : pieces) m = std::max(m, p.getMaxAccRate());
+        return m;
+    }
+    bool checkMaxVelRate(double maxVelRate) const {
+        for (const auto& p : pieces)
+            if (!p.checkMaxVelRate(maxVelRate)) return false;
+        return true;
+    }
+    bool checkMaxAccRate(double maxAccRate) const {
+        for (const auto& p : pieces)
+            if (!p.checkMaxAccRate(maxAccRate)) return false;
+        return true;
+    }
+    // junction states (trajectory.hpp:457-515): juncIdx 0..N, the start of piece juncIdx (or the end of the last piece)
+    std::array<double, 3> getJuncPos(int j) const { return j < getPieceNum() ? pieces[j].getPos(0.0) : pieces[j - 1].getPos(pieces[j - 1].getDuration()); }
+    std::array<double, 3> getJuncVel(int j) const { return j < getPieceNum() ? pieces[j].getVel(0.0) : pieces[j - 1].getVel(pieces[j - 1].getDuration()); }
+    std::array<double, 3> getJuncAcc(int j) const { return j < getPieceNum() ? pieces[j].getAcc(0.0) : pieces[j - 1].getAcc(pieces[j - 1].getDuration()); }
 };
+
+// ---- wire format (se3_planner.cpp:31-58 traj2msg -> quadrotor_msgs/PolynomialTrajectory.msg) -----------
+// The payload fields of the message the planner publishes to traj_server, without the ROS header: per piece the
+// duration-NORMALISED position coefficients, highest order first, one array per axis.  A ROS caller copies these fields
+// into quadrotor_msgs::PolynomialTrajectory one to one.
+struct PolynomialTrajectoryFields {
+    enum : unsigned { ACTION_ADD = 1 };
+    unsigned action = ACTION_ADD;
+    unsigned num_order = 5, num_segment = 0;
+    double start_yaw = 0.0, final_yaw = 0.0, mag_coeff = 1.0;
+    std::vector<double> coef_x, coef_y, coef_z, time;
+    std::vector<unsigned> order;
+};
+inline PolynomialTrajectoryFields traj2fields(const Trajectory& traj) {
+    PolynomialTrajectoryFields m;
+    m.num_segment = (unsigned)traj.getPieceNum();
+    m.num_order = m.num_segment ? (unsigned)traj[0].getOrder() : 5u;
+    for (unsigned i = 0; i < m.num_segment; i++) {
+        const auto n = traj[(int)i].normalizePosCoeffMat();
+        for (int j = 0; j <= traj[(int)i].getOrder(); j++) {
+            m.coef_x.push_back(n[3 * j + 0]);
+            m.coef_y.push_back(n[3 * j + 1]);
+            m.coef_z.push_back(n[3 * j + 2]);
+        }
+        m.time.push_back(traj[(int)i].getDuration());
+        m.order.push_back((unsigned)traj[(int)i].getOrder());
+    }
+    return m;
+}
 
 // ---- the optimiser --------------------------------------------------------------------------------
 class SE3GCOPTER {

@@ -28,3 +28,16 @@ def test_facade_runs_the_reference_call_sequence():
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Final cost" in r.stdout and "infeasible corridor rejected: 1" in r.stdout
+
+
+def test_trajectory_containers_cpu():
+    """Piece / Trajectory helpers the planner calls downstream: exact max velocity / acceleration rates
+    (root isolation instead of root_finder.hpp) against 2e5-point sampling, checkMax*Rate, getRotation, normalised
+    coefficients, junction states.  Header-only, C++14, no CUDA and no libfrx needed."""
+    exe = os.path.join(ROOT, "tests", "cpp", "trajectory_check")
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "trajectory_check.cpp"),
+           "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
