@@ -1,12 +1,14 @@
 // The three kernels of one batched cost+gradient evaluation (SE3GCOPTER::objectiveFunc,
 // se3gcopter_cpu.hpp "CPU.hpp" :961-1000), hand-written for sm_100a, fp64 throughout:
 //
-//   K1 minco_forward_kernel   x=(tau,xi) -> T, q -> banded MINCO system -> LU -> c      (one warp / trajectory)
+//   K1 minco_forward_kernel   x=(tau,xi) -> T, q -> banded MINCO system -> LU -> c      (one 2-warp CTA / trajectory:
+//                             pivot warp + feeder warp over a shared-memory ring of the band)
 //        forwardT CPU.hpp:626, splitToFineT :930, forwardP :729, MINCO_S3::generate :425,
 //        BandedSystem::factorizeLU/solve trajectory.hpp:655/692
 //   K2 penalty_kernel         c -> per-piece penalty integral, dJ/dc, dJ/dT, jerk energy  (samples x pieces x batch)
 //        MINCO_S3::addTimeIntPenalty CPU.hpp:188-408, getTrajJerkCost :507, addGradJbyT :65, addGradJbyC :80
-//   K3 minco_backward_kernel  dJ/dc -> adjoint solve -> dJ/dT, dJ/dq -> dJ/d(tau,xi), cost (one warp / trajectory)
+//   K3 minco_backward_kernel  dJ/dc -> adjoint solve -> dJ/dT, dJ/dq -> dJ/d(tau,xi), cost (one 2-warp CTA / trajectory:
+//                             sweep warp + cp.async producer warp streaming the factors)
 //        BandedSystem::solveAdj trajectory.hpp:724, addPropCtoT CPU.hpp:104, addPropCtoP :154,
 //        mergeToCoarseGradT :946, addLayerTGrad :816, addLayerPGrad :897, rho terms :988-989
 //
