@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--solve-batch", type=int, default=256, help="trajectories of the solves/sec leg (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="--impl reference: CPU budget of the whole run (all steps)")
     return ap.parse_args()
 
 
@@ -146,9 +147,9 @@ def run_reference(a):
     # calibrate UNDER LOAD (all threads busy): per-evaluation time rises with SMT / memory contention
     cal = ob.time_evals_mt(oracles, xs, 20, ncpu) / 20.0  # seconds for one evaluation of every trajectory on all threads
     # second stage: ~3 s sustained (short bursts run several times faster per evaluation than a saturated box)
-    r2 = max(20, int(3.0 / max(cal, 1e-6)))
+    r2 = max(20, int(min(3.0, a.ref_seconds / 10.0) / max(cal, 1e-6)))
     cal = max(cal, ob.time_evals_mt(oracles, xs, r2, ncpu) / r2)
-    per_step_budget = 60.0 / max(1, a.steps + a.warmup)
+    per_step_budget = a.ref_seconds / max(1, a.steps + a.warmup)
     reps = max(1, int(per_step_budget / max(cal, 1e-6)))
     for _ in range(a.warmup):
         ob.time_evals_mt(oracles, xs, reps, ncpu)
