@@ -338,7 +338,88 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 
     PHASE_MARK(0, 2);
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
-#ifndef FRX_EXACT
+#if !defined(FRX_EXACT) && defined(FRX_K1_NP)
+    // EXPERIMENTAL, not built by default (build with FRX_NVCC_EXTRA=-DFRX_K1_NP=3 or 6; NOT yet validated on a GPU):
+    // NP pivots per trip, the generalisation of the two-pivot loop below.  Every lane recomputes, in registers, the LU of
+    // the NP x NP diagonal block of the pivot rows and those rows' updates at ITS columns, so a trip needs one
+    // shared-memory load round and one store round.  Per element the operations are the sequential elimination's
+    // (pivots ascending), i.e. the results must be bit-identical to the default build.  The slot algebra is checked on the
+    // CPU by scripts/proto/k1_piece_trip_emulation.py (NP = 2, 3, 6 against a dense no-pivot LU).
+    if (warp == 0) {
+        constexpr int NP = FRX_K1_NP;
+        static_assert(NP >= 2 && NP <= 6 && 6 % NP == 0, "pivots per trip must divide a piece");
+        const int r = lane / 3, cg = lane - 3 * r;  // row k0+NP+r; columns k0+NP+cg, k0+NP+3+cg; right-hand side cg
+        constexpr unsigned RB = RING * BW * 8;
+        char* const rb = reinterpret_cast<char*>(ring);
+        const bool act = lane < 18;
+        unsigned ok = 0;  // byte offset of the first pivot row k0 of the trip
+        for (int j = 0; j < M; j++) {
+#pragma unroll 1
+            for (int tr = 0; tr < 6 / NP; tr++) {
+                if (act) {
+                    double D[NP][NP], rcp[NP], Cx[NP], Cy[NP], Rr[NP], Mm[NP];
+                    double* Pa[NP];
+#pragma unroll
+                    for (int a = 0; a < NP; a++) Pa[a] = reinterpret_cast<double*>(rb + ((ok + a * BW * 8) & (RB - 1)));
+                    double* Rw = reinterpret_cast<double*>(rb + ((ok + (NP + r) * BW * 8) & (RB - 1)));
+#pragma unroll
+                    for (int a = 0; a < NP; a++) {
+#pragma unroll
+                        for (int b = 0; b < NP; b++) D[a][b] = Pa[a][b - a + 6];
+                        Cx[a] = (a >= NP + cg - 6) ? Pa[a][NP + cg - a + 6] : 0.0;  // in-band columns only
+                        Cy[a] = (a >= NP + cg - 3) ? Pa[a][NP + cg - a + 9] : 0.0;
+                        Rr[a] = Pa[a][13 + cg];
+                    }
+#pragma unroll
+                    for (int b = 0; b < NP; b++) Mm[b] = (b >= NP + r - 6) ? Rw[b - NP - r + 6] : 0.0;
+                    double Ex = Rw[6 + cg - r], Ey = Rw[9 + cg - r], Er = Rw[13 + cg];
+                    __syncwarp(0x3ffffu);  // every lane holds its operands: the stores below may overwrite them
+                    rcp[0] = D[0][0];      // slot 6 of the first pivot row holds 1/u already
+#pragma unroll
+                    for (int p = 0; p < NP; p++) {
+                        if (p > 0) rcp[p] = fast_rcp(D[p][p]);
+#pragma unroll
+                        for (int a = p + 1; a < NP; a++) {
+                            const double l = D[a][p] * rcp[p];
+                            D[a][p] = l;
+#pragma unroll
+                            for (int b = p + 1; b < NP; b++) D[a][b] -= l * D[p][b];
+                            Cx[a] -= l * Cx[p], Cy[a] -= l * Cy[p], Rr[a] -= l * Rr[p];
+                        }
+                        const double l = Mm[p] * rcp[p];
+                        Mm[p] = l;
+#pragma unroll
+                        for (int b = p + 1; b < NP; b++) Mm[b] -= l * D[p][b];
+                        Ex -= l * Cx[p], Ey -= l * Cy[p], Er -= l * Rr[p];
+                    }
+                    Rw[6 + cg - r] = (lane == 0) ? fast_rcp(Ex) : Ex;  // lane 0 owns the next trip's first pivot: store 1/u
+                    Rw[9 + cg - r] = Ey;
+                    Rw[13 + cg] = Er;
+                    if (cg == 0) {
+#pragma unroll
+                        for (int b = 0; b < NP; b++)
+                            if (b >= NP + r - 6) Rw[b - NP - r + 6] = Mm[b];
+                    }
+#pragma unroll
+                    for (int a = 0; a < NP; a++) {
+                        if (r == a) {  // lanes (a, cg) publish the finished pivot row a
+                            if (a >= NP + cg - 6) Pa[a][NP + cg - a + 6] = Cx[a];
+                            if (a >= NP + cg - 3) Pa[a][NP + cg - a + 9] = Cy[a];
+                            Pa[a][13 + cg] = Rr[a];
+                            if (cg == 0) {
+#pragma unroll
+                                for (int b = 0; b < NP; b++) Pa[a][b - a + 6] = (b == a) ? rcp[a] : D[a][b];
+                            }
+                        }
+                    }
+                }
+                ok = (ok + NP * BW * 8) & (RB - 1);
+                __syncwarp();
+            }
+            cta_bar64();
+        }
+    } else {
+#elif !defined(FRX_EXACT)
     if (warp == 0) {
         // TWO pivots (k, k+1) per trip: every lane recomputes the update of row k+1 by pivot k for the columns it needs
         // (and 1/u_{k+1,k+1}), so the pair costs one shared-memory round trip instead of two.  The arithmetic per element is
