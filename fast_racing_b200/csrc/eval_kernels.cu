@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <cstdlib>
+#include <mutex>
 
 #include "device_batch.cuh"
 
@@ -41,43 +42,6 @@ __device__ __forceinline__ double c2_forward(double t) {  // CPU.hpp:639-641
     return t > 0.0 ? ((0.5 * t + 1.0) * t + 1.0) : 1.0 / ((0.5 * t - 1.0) * t + 1.0);
 }
 
-// K1 ---------------------------------------------------------------------------------------------
-// One trajectory per CTA of two warps.
-//   warp 0  runs the dependent chain: the 6M-1 pivots of the banded LU (trajectory.hpp:655-687) with the
-//           forward substitution of the three right-hand sides fused in (:695-705), on a 32-row ring of the
-//           band in shared memory; then the back substitution (:706-717).
-//   warp 1  keeps the chain fed: it fills the rows of the junction two pieces ahead from a constant entry
-//           table (MINCO_S3::generate, CPU.hpp:437-499), and retires finished rows: LU factors to global
-//           memory for the adjoint solve of K3, (1/u_ii, U row, y) into a compact shared store for the back
-//           substitution.  The warps meet at one barrier per piece (6 pivots).
-// Only ~(4 + 0.5 M) KB of shared memory per trajectory, so a 1024-trajectory batch is resident in one wave.
-//
-// Ring row layout (16 doubles): [0..5] multipliers l_{i,i-6..i-1} | [6] 1/u_ii once final (the diagonal
-// before) | [7..12] u_{i,i+1..i+6} | [13..15] right-hand side (x,y,z).  Rows are retired to bv.lu in the
-// same layout.
-#define RING 32
-#ifdef FRX_EXACT
-#define UST 10  // reference-order build: u_ii, u_{i,i+1..i+6}, y_{x,y,z} (division kept in the back substitution)
-#else
-#define UST 9  // compact store per row, pre-multiplied by 1/u_ii: u_{i,i+1..i+6}/u_ii, y_{x,y,z}/u_ii
-#endif
-
-// Entry tables of one junction block (rows 6i+3 .. 6i+8, CPU.hpp:446-476): value = coef * T^pow at
-// (row offset, band slot = column - row + 6).
-__device__ const int JR[31] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
-__device__ const int JS[31] = {6, 7, 8, 12, 6, 7, 12, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 6, 0, 1, 2, 3, 6};
-__device__ const double JC[31] = {6.0, 24.0, 60.0, -6.0, 24.0, 120.0, -24.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
-                              1.0, 1.0, -1.0, 1.0, 2.0, 3.0, 4.0, 5.0, -1.0, 2.0, 6.0, 12.0, 20.0, -2.0};
-__device__ const int JP[31] = {0, 1, 2, 0, 0, 1, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 0};
-// Tail block (rows 6M-3 .. 6M-1, CPU.hpp:481-495), T of the last piece.
-__device__ const int TR[15] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2};
-__device__ const int TS[15] = {3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 3, 4, 5, 6};
-__device__ const double TC[15] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 4.0, 5.0, 2.0, 6.0, 12.0, 20.0};
-__device__ const int TP[15] = {0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3};
-
-__device__ __forceinline__ double pick_pow(int p, double T1, double T2, double T3, double T4, double T5) {
-    return p == 0 ? 1.0 : (p == 1 ? T1 : (p == 2 ? T2 : (p == 3 ? T3 : (p == 4 ? T4 : T5))));
-}
 // 1/x without the slow-path branches of the compiler's division: hardware seed + two Newton steps (~1 ulp).
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
@@ -151,6 +115,41 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+#ifdef FRX_EXACT  // reference-order build only: the banded system in the reference's own elimination order
+// K1 ---------------------------------------------------------------------------------------------
+// One trajectory per CTA of two warps.
+//   warp 0  runs the dependent chain: the 6M-1 pivots of the banded LU (trajectory.hpp:655-687) with the
+//           forward substitution of the three right-hand sides fused in (:695-705), on a 32-row ring of the
+//           band in shared memory; then the back substitution (:706-717).
+//   warp 1  keeps the chain fed: it fills the rows of the junction two pieces ahead from a constant entry
+//           table (MINCO_S3::generate, CPU.hpp:437-499), and retires finished rows: LU factors to global
+//           memory for the adjoint solve of K3, (1/u_ii, U row, y) into a compact shared store for the back
+//           substitution.  The warps meet at one barrier per piece (6 pivots).
+// Only ~(4 + 0.5 M) KB of shared memory per trajectory, so a 1024-trajectory batch is resident in one wave.
+//
+// Ring row layout (16 doubles): [0..5] multipliers l_{i,i-6..i-1} | [6] 1/u_ii once final (the diagonal
+// before) | [7..12] u_{i,i+1..i+6} | [13..15] right-hand side (x,y,z).  Rows are retired to bv.lu in the
+// same layout.
+#define RING 32
+#define UST 10  // reference-order build: u_ii, u_{i,i+1..i+6}, y_{x,y,z} (division kept in the back substitution)
+
+// Entry tables of one junction block (rows 6i+3 .. 6i+8, CPU.hpp:446-476): value = coef * T^pow at
+// (row offset, band slot = column - row + 6).
+__device__ const int JR[31] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5};
+__device__ const int JS[31] = {6, 7, 8, 12, 6, 7, 12, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 6, 0, 1, 2, 3, 6};
+__device__ const double JC[31] = {6.0, 24.0, 60.0, -6.0, 24.0, 120.0, -24.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
+                              1.0, 1.0, -1.0, 1.0, 2.0, 3.0, 4.0, 5.0, -1.0, 2.0, 6.0, 12.0, 20.0, -2.0};
+__device__ const int JP[31] = {0, 1, 2, 0, 0, 1, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 0, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 0};
+// Tail block (rows 6M-3 .. 6M-1, CPU.hpp:481-495), T of the last piece.
+__device__ const int TR[15] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2};
+__device__ const int TS[15] = {3, 4, 5, 6, 7, 8, 3, 4, 5, 6, 7, 3, 4, 5, 6};
+__device__ const double TC[15] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 3.0, 4.0, 5.0, 2.0, 6.0, 12.0, 20.0};
+__device__ const int TP[15] = {0, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 0, 1, 2, 3};
+
+__device__ __forceinline__ double pick_pow(int p, double T1, double T2, double T3, double T4, double T5) {
+    return p == 0 ? 1.0 : (p == 1 ? T1 : (p == 2 ? T2 : (p == 3 ? T3 : (p == 4 ? T4 : T5))));
+}
+
 // Per-lane entry of the fill tables (lane e writes entry e of a junction / tail block).
 struct FillLane {
     int jr, js, jp, tr, ts, tp;
@@ -191,11 +190,7 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
     for (int e = lane; e < cnt * UST; e += 32) {
         const int rr = e / UST, q = e - UST * rr;
         const double* rw = ring + ((row0 + rr) & (RING - 1)) * BW;
-#ifdef FRX_EXACT
         ust[(size_t)(row0 + rr) * UST + q] = rw[6 + q];  // diagonal, upper band, y: unscaled
-#else
-        ust[(size_t)(row0 + rr) * UST + q] = rw[7 + q] * rw[6];  // x_i = y_i/u_ii - sum_t (u_{i,i+t}/u_ii) x_{i+t}
-#endif
     }
 }
 
@@ -254,7 +249,6 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         bv.T[p0 + i] = Tv;
         stage[4 * i] = Tv;
     }
-#ifdef FRX_EXACT
     for (int i = tid; i < M - 1; i += 64) {  // one thread per waypoint, sums in the reference's order
         const int k = bv.wp_vert_cnt[p0 + i] - 1;
         const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
@@ -275,42 +269,6 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         const double qv[3] = {qx + V[0], qy + V[1], qz + V[2]};
         for (int d = 0; d < 3; d++) bv.q[3 * (size_t)(p0 + i) + d] = stage[4 * i + 1 + d] = qv[d];
     }
-#else
-    {   // four lanes per waypoint (sector-sized coalesced reads of xi and V, many loads in flight), one pass:
-        //   q = v0 + sc^2 * sum_a V_{a+1} xi_a^2,  sc = 2 / (1 + |xi|^2)
-        const int grp = tid >> 2, l4 = tid & 3;
-        const unsigned gmask = 0xFu << (lane & ~3);
-        for (int i = grp; i < M - 1; i += 16) {
-            const int k = wpi[i];
-            const double* V = bv.verts + 3 * (size_t)wpi[2 * M + i];
-            const double* xi = x + dimT + wpi[M + i];
-            double sn = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-#pragma unroll 4
-            for (int a = l4; a < k; a += 4) {
-                const double xa = xi[a], x2 = xa * xa;
-                sn += x2;
-                sx += V[3 * (a + 1) + 0] * x2;
-                sy += V[3 * (a + 1) + 1] * x2;
-                sz += V[3 * (a + 1) + 2] * x2;
-            }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                sn += __shfl_xor_sync(gmask, sn, o);
-                sx += __shfl_xor_sync(gmask, sx, o);
-                sy += __shfl_xor_sync(gmask, sy, o);
-                sz += __shfl_xor_sync(gmask, sz, o);
-            }
-            const double sc = 2.0 / (1.0 + sn), sc2 = sc * sc;
-            const double sd_ = l4 == 0 ? sx : (l4 == 1 ? sy : sz);
-            bv.wpw[4 * (size_t)(p0 + i) + l4] = (l4 == 3) ? sn : sd_;  // reused by addLayerPGrad in K3
-            if (l4 < 3) {
-                const double qd = V[l4] + sc2 * sd_;
-                bv.q[3 * (size_t)(p0 + i) + l4] = qd;
-                stage[4 * i + 1 + l4] = qd;
-            }
-        }
-    }
-#endif
     __syncthreads();  // the fills read the staged T and q
     PHASE_MARK(0, 1);
 
@@ -331,185 +289,10 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         fill_block(ring, bv, b, M, 1, lane, fl, loadT(1), loadq(1));
     }
     __syncthreads();
-#ifndef FRX_EXACT
-    if (tid == 0) ring[6] = 1.0 / ring[6];
-#endif
     __syncthreads();
 
     PHASE_MARK(0, 2);
     // ---- phases: piece j = pivots 6j .. 6j+5 ----
-#if !defined(FRX_EXACT) && defined(FRX_K1_NP)
-    // EXPERIMENTAL, not built by default (build with FRX_NVCC_EXTRA=-DFRX_K1_NP=3 or 6; NOT yet validated on a GPU):
-    // NP pivots per trip, the generalisation of the two-pivot loop below.  Every lane recomputes, in registers, the LU of
-    // the NP x NP diagonal block of the pivot rows and those rows' updates at ITS columns, so a trip needs one
-    // shared-memory load round and one store round.  Per element the operations are the sequential elimination's
-    // (pivots ascending), i.e. the results must be bit-identical to the default build.  The slot algebra is checked on the
-    // CPU by scripts/proto/k1_piece_trip_emulation.py (NP = 2, 3, 6 against a dense no-pivot LU).
-    if (warp == 0) {
-        constexpr int NP = FRX_K1_NP;
-        static_assert(NP >= 2 && NP <= 6 && 6 % NP == 0, "pivots per trip must divide a piece");
-        const int r = lane / 3, cg = lane - 3 * r;  // row k0+NP+r; columns k0+NP+cg, k0+NP+3+cg; right-hand side cg
-        constexpr unsigned RB = RING * BW * 8;
-        char* const rb = reinterpret_cast<char*>(ring);
-        const bool act = lane < 18;
-        unsigned ok = 0;  // byte offset of the first pivot row k0 of the trip
-        for (int j = 0; j < M; j++) {
-#pragma unroll 1
-            for (int tr = 0; tr < 6 / NP; tr++) {
-                if (act) {
-                    double D[NP][NP], rcp[NP], Cx[NP], Cy[NP], Rr[NP], Mm[NP];
-                    double* Pa[NP];
-#pragma unroll
-                    for (int a = 0; a < NP; a++) Pa[a] = reinterpret_cast<double*>(rb + ((ok + a * BW * 8) & (RB - 1)));
-                    double* Rw = reinterpret_cast<double*>(rb + ((ok + (NP + r) * BW * 8) & (RB - 1)));
-#pragma unroll
-                    for (int a = 0; a < NP; a++) {
-#pragma unroll
-                        for (int b = 0; b < NP; b++) D[a][b] = Pa[a][b - a + 6];
-                        Cx[a] = (a >= NP + cg - 6) ? Pa[a][NP + cg - a + 6] : 0.0;  // in-band columns only
-                        Cy[a] = (a >= NP + cg - 3) ? Pa[a][NP + cg - a + 9] : 0.0;
-                        Rr[a] = Pa[a][13 + cg];
-                    }
-#pragma unroll
-                    for (int b = 0; b < NP; b++) Mm[b] = (b >= NP + r - 6) ? Rw[b - NP - r + 6] : 0.0;
-                    double Ex = Rw[6 + cg - r], Ey = Rw[9 + cg - r], Er = Rw[13 + cg];
-                    __syncwarp(0x3ffffu);  // every lane holds its operands: the stores below may overwrite them
-                    rcp[0] = D[0][0];      // slot 6 of the first pivot row holds 1/u already
-#pragma unroll
-                    for (int p = 0; p < NP; p++) {
-                        if (p > 0) rcp[p] = fast_rcp(D[p][p]);
-#pragma unroll
-                        for (int a = p + 1; a < NP; a++) {
-                            const double l = D[a][p] * rcp[p];
-                            D[a][p] = l;
-#pragma unroll
-                            for (int b = p + 1; b < NP; b++) D[a][b] -= l * D[p][b];
-                            Cx[a] -= l * Cx[p], Cy[a] -= l * Cy[p], Rr[a] -= l * Rr[p];
-                        }
-                        const double l = Mm[p] * rcp[p];
-                        Mm[p] = l;
-#pragma unroll
-                        for (int b = p + 1; b < NP; b++) Mm[b] -= l * D[p][b];
-                        Ex -= l * Cx[p], Ey -= l * Cy[p], Er -= l * Rr[p];
-                    }
-                    Rw[6 + cg - r] = (lane == 0) ? fast_rcp(Ex) : Ex;  // lane 0 owns the next trip's first pivot: store 1/u
-                    Rw[9 + cg - r] = Ey;
-                    Rw[13 + cg] = Er;
-                    if (cg == 0) {
-#pragma unroll
-                        for (int b = 0; b < NP; b++)
-                            if (b >= NP + r - 6) Rw[b - NP - r + 6] = Mm[b];
-                    }
-#pragma unroll
-                    for (int a = 0; a < NP; a++) {
-                        if (r == a) {  // lanes (a, cg) publish the finished pivot row a
-                            if (a >= NP + cg - 6) Pa[a][NP + cg - a + 6] = Cx[a];
-                            if (a >= NP + cg - 3) Pa[a][NP + cg - a + 9] = Cy[a];
-                            Pa[a][13 + cg] = Rr[a];
-                            if (cg == 0) {
-#pragma unroll
-                                for (int b = 0; b < NP; b++) Pa[a][b - a + 6] = (b == a) ? rcp[a] : D[a][b];
-                            }
-                        }
-                    }
-                }
-                ok = (ok + NP * BW * 8) & (RB - 1);
-                __syncwarp();
-            }
-            cta_bar64();
-        }
-    } else {
-#elif !defined(FRX_EXACT)
-    if (warp == 0) {
-        // TWO pivots (k, k+1) per trip: every lane recomputes the update of row k+1 by pivot k for the columns it needs
-        // (and 1/u_{k+1,k+1}), so the pair costs one shared-memory round trip instead of two.  The arithmetic per element is
-        // exactly the sequential one: a_ij -= l_ik u_kj, then a_ij -= l_i,k+1 u_k+1,j.
-        // Lane (r, cg): row i = k+2+r, columns k+2+cg and k+5+cg, right-hand side cg.  Slot of column c in row i: c - i + 6.
-        const int r = lane / 3, cg = lane - 3 * r;
-        constexpr unsigned RB = RING * BW * 8;  // ring size in bytes (power of two)
-        char* const rb = reinterpret_cast<char*>(ring);
-        const bool act = lane < 18;
-        unsigned ok = 0;  // byte offset of pivot row k
-        PHASE_ACC_DECL;
-#ifdef FRX_PHASE_CLK
-        long long pc_[4] = {0, 0, 0, 0}, c0_ = clock64();
-#endif
-        for (int j = 0; j < M; j++) {
-#ifdef FRX_PHASE_CLK
-            c0_ = clock64();
-#endif
-#pragma unroll 1
-            for (int pr = 0; pr < 3; pr++) {
-                if (act) {
-                    const double* R0 = reinterpret_cast<const double*>(rb + ok);
-                    double* R1 = reinterpret_cast<double*>(rb + ((ok + BW * 8) & (RB - 1)));
-                    double* Rw = reinterpret_cast<double*>(rb + ((ok + (2 + r) * BW * 8) & (RB - 1)));
-                    const double rcp0 = R0[6], u01 = R0[7], u0a = R0[8 + cg], u0b = (cg < 2) ? R0[11 + cg] : 0.0, y0 = R0[13 + cg];
-                    const double a10 = R1[5], a11 = R1[6], a1a = R1[7 + cg], a1b = R1[10 + cg], y1r = R1[13 + cg];
-                    const double ai0 = (r < 5) ? Rw[4 - r] : 0.0, ai1 = Rw[5 - r];
-                    const double ea = Rw[6 + cg - r], eb = Rw[9 + cg - r], ey = Rw[13 + cg];
-                    __syncwarp(0x3ffffu);  // every lane holds its operands: the stores below may overwrite them
-#ifdef FRX_PHASE_CLK
-                    const long long c1_ = clock64();
-                    pc_[0] += (c1_ - c0_) + (long long)(ai0 * 0.0);  // operand use pins the loads before this mark
-#endif
-                    // row k+1 by pivot k
-                    const double l10 = a10 * rcp0;  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
-                    const double u11 = a11 - l10 * u01;
-                    const double rcp1 = fast_rcp(u11);
-                    const double u1a = a1a - l10 * u0a, u1b = a1b - l10 * u0b, y1 = y1r - l10 * y0;
-                    // row i by pivots k and k+1
-                    const double li0 = ai0 * rcp0;
-                    const double ti1 = ai1 - li0 * u01;
-                    const double li1 = ti1 * rcp1;
-#ifdef FRX_PHASE_CLK
-                    const long long c2_ = clock64() + (long long)(rcp1 * 0.0);
-                    pc_[1] += c2_ - c1_;
-#endif
-                    const double va = (ea - li0 * u0a) - li1 * u1a;
-                    const double vb = (eb - li0 * u0b) - li1 * u1b;
-                    const double vy = (ey - li0 * y0) - li1 * y1;
-#ifdef FRX_PHASE_CLK
-                    const long long c3_ = clock64() + (long long)(va * 0.0);
-                    pc_[2] += c3_ - c2_;
-#endif
-                    // Lane 0 (r = 0, cg = 0) owns the next pivot u = va and stores 1/u.  With w = ea - li0 u0a:
-                    //   u = w - (ti1/u11) u1a = (w u11 - ti1 u1a) / u11   =>   1/u = u11 / (w u11 - ti1 u1a),
-                    // whose reciprocal does not wait for 1/u11 (the two reciprocals of a pair run concurrently).
-                    const double rnx = u11 * fast_rcp((ea - li0 * u0a) * u11 - ti1 * u1a);
-                    Rw[6 + cg - r] = (lane == 0) ? rnx : va;
-                    Rw[9 + cg - r] = vb;
-                    Rw[13 + cg] = vy;
-                    if (cg == 0) {
-                        if (r < 5) Rw[4 - r] = li0;
-                        Rw[5 - r] = li1;
-                    }
-                    if (r == 0) {  // the finished row k+1
-                        R1[7 + cg] = u1a, R1[10 + cg] = u1b, R1[13 + cg] = y1;
-                        if (cg == 0) R1[5] = l10, R1[6] = rcp1;
-                    }
-                }
-                ok = (ok + 2 * BW * 8) & (RB - 1);
-                __syncwarp();
-#ifdef FRX_PHASE_CLK
-                {
-                    const long long c4_ = clock64();
-                    pc_[3] += c4_ - c0_;
-                    c0_ = c4_;
-                }
-#endif
-            }
-            PHASE_ACC_WORK();
-            cta_bar64();
-            PHASE_ACC_WAIT();
-        }
-        PHASE_ACC_STORE(0);
-#ifdef FRX_PHASE_CLK
-        if (blockIdx.x == gridDim.x / 2 && lane == 0)
-            for (int q = 0; q < 4; q++) g_phase_clk[10 + q] = pc_[q];
-#endif
-    } else {
-#else
     if (warp == 0) {
         const int r = lane / 3, cg = lane - 3 * r;
         constexpr unsigned RB = RING * BW * 8;  // ring size in bytes (power of two)
@@ -529,19 +312,11 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
                     double* pa = reinterpret_cast<double*>(rb + oi + cA);
                     double* pb = reinterpret_cast<double*>(rb + oi + cB);
                     double* pc = reinterpret_cast<double*>(rb + oi + cC);
-#ifdef FRX_EXACT
                     const double l = *pa / rk[6];  // a_ik / u_kk as the reference (trajectory.hpp:667)
-#else
-                    const double l = *pa * rk[6];  // a_ik * (1/u_kk); exact zeros stay exact zeros (trajectory.hpp:665)
-#endif
                     const double v0 = pb[0] - l * rk2[7];
                     const double v1 = pb[3] - l * rk2[10];
                     const double v2 = *pc - l * rk2[13];
-#ifdef FRX_EXACT
                     pb[0] = v0;
-#else
-                    pb[0] = (lane == 0) ? fast_rcp(v0) : v0;  // lane 0 (r = 0, cg = 0) owns the next pivot: store 1/u
-#endif
                     pb[3] = v1;
                     *pc = v2;
                     *pend = l_pend;  // multiplier of the PREVIOUS step (nobody reads column k-1 any more)
@@ -556,7 +331,6 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             cta_bar64();
         }
     } else {
-#endif
         // The feeder's per-phase work is straight-line code on per-lane constants (K1 is issue-bound with seven CTAs per SM):
         //   fill     slot e = lane + 32 t (t < 3) of the 6 x 16 junction block holds  fc[t] * T^fp[t]  (0 for non-entries),
         //            except the waypoint row's right-hand side (row 2, columns 13..15 = lanes 13..15 at t = 1);
@@ -604,19 +378,11 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
                 }
                 {
                     const double* rw = ring + ((row0 + ur0) & (RING - 1)) * BW;
-#ifdef FRX_EXACT
                     ust[(size_t)(row0 + ur0) * UST + uq0] = rw[6 + uq0];
-#else
-                    ust[(size_t)(row0 + ur0) * UST + uq0] = rw[7 + uq0] * rw[6];
-#endif
                 }
                 if (u1on) {
                     const double* rw = ring + ((row0 + ur1) & (RING - 1)) * BW;
-#ifdef FRX_EXACT
                     ust[(size_t)(row0 + ur1) * UST + uq1] = rw[6 + uq1];
-#else
-                    ust[(size_t)(row0 + ur1) * UST + uq1] = rw[7 + uq1] * rw[6];
-#endif
                 }
             }
             PHASE_ACC_WORK();
@@ -642,16 +408,10 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             for (int u = 5; u >= 0; u--) {
                 const int i = base + u;
                 const double* Ui = ust + (size_t)i * UST;
-#ifdef FRX_EXACT
                 double acc = Ui[7 + d];
 #pragma unroll
                 for (int t = 6; t >= 1; t--) acc -= Ui[t] * w[(u + t) % 6];
                 acc = acc / Ui[0];
-#else
-                double acc = Ui[6 + d];
-#pragma unroll
-                for (int t = 6; t >= 1; t--) acc -= Ui[t - 1] * w[(u + t) % 6];
-#endif
                 w[u] = acc;
                 cg_[3 * i + d] = acc;
             }
@@ -659,6 +419,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     }
     PHASE_MARK(0, 5);
 }
+#endif  // FRX_EXACT (banded kernels)
 
 // K2 ---------------------------------------------------------------------------------------------
 // Per-sample work of MINCO_S3::addTimeIntPenalty (CPU.hpp:188-408), restructured around ADJOINT
@@ -1196,6 +957,7 @@ __global__ void __launch_bounds__(32) penalty_exact_kernel(BatchView bv) {
 }
 #endif  // FRX_EXACT
 
+#ifdef FRX_EXACT  // reference-order build only: the banded system in the reference's own elimination order
 // K3 ---------------------------------------------------------------------------------------------
 // One trajectory per CTA of two warps.  The LU factors written by K1 (bv.lu, 16 doubles per row) are
 // streamed through a ring of 6-row blocks in shared memory: warp 1 issues cp.async copies LOOKAHEAD
@@ -1343,11 +1105,7 @@ __global__ void __launch_bounds__(64)
 #define UCOEF(u, s) (((u) - (s) >= 0) ? cur[((u) - (s)) * BW + 6 + (s)] : prv[((u) - (s) + 6) * BW + 6 + (s)])
 #define PRE1(u) (((((bs[3 * (u)] - UCOEF(u, 6) * w[((u) + 0) % 6]) - UCOEF(u, 5) * w[((u) + 1) % 6]) - UCOEF(u, 4) * w[((u) + 2) % 6]) - \
                   UCOEF(u, 3) * w[((u) + 3) % 6]) - UCOEF(u, 2) * w[((u) + 4) % 6])
-#ifdef FRX_EXACT
 #define FIN1(u, pre) (((pre)-UCOEF(u, 1) * w[((u) + 5) % 6]) / cur[(u) * BW + 6])
-#else
-#define FIN1(u, pre) (((pre)-UCOEF(u, 1) * w[((u) + 5) % 6]) * cur[(u) * BW + 6])
-#endif
     {
         double w[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // z_{i-6..i-1} of this lane's right-hand side: z_j at w[j mod 6]
         for (int p = 0; p < M; p++) {
@@ -1525,7 +1283,6 @@ __global__ void __launch_bounds__(64)
     }
     PHASE_MARK(2, 6);
     // ---- addLayerPGrad (CPU.hpp:897-928) ----
-#ifdef FRX_EXACT
     for (int i = tid; i < M - 1; i += 64) {
         const int k = bv.wp_vert_cnt[p0 + i] - 1;
         const double* V = bv.verts + 3 * (size_t)bv.wp_vert_off[p0 + i];
@@ -1550,7 +1307,518 @@ __global__ void __launch_bounds__(64)
             gxi[a] = gd * 2.0 / q1 - xi[a] * 4.0 * gdot / q1s;
         }
     }
-#else
+    PHASE_MARK(2, 7);
+}
+#endif  // FRX_EXACT (banded kernels)
+
+#ifndef FRX_EXACT
+// =================================================================================================
+// Fast build: the MINCO map (q,T) -> c and its adjoint through the REDUCED system.
+//
+// MINCO_S3::generate (CPU.hpp:425-505) solves a 6M x 6M banded system whose rows are: head / tail states, the waypoints,
+// C^2 continuity of position at the junctions, and continuity of jerk and snap.  A quintic piece is fixed by the states
+// (p, v, a) at its two ends, so with the node states as unknowns every row except jerk / snap continuity holds by
+// construction, the node positions are the waypoints, and what remains are the node velocities and accelerations
+// y_j = (v_j, a_j), j = 1..M-1.  Jerk / snap continuity at node j are the stationarity conditions of the jerk energy
+// w.r.t. (a_j, v_j) (d/da_end of 1/2 int jerk^2 = jerk(T), d/dv_end = -snap(T), d/dp_end = crackle(T)), hence
+//
+//        S(T) y = r(q, T),        S symmetric positive definite, block tridiagonal, 2 x 2 blocks,
+//        D_j = [192 (1/Ta^3 + 1/Tb^3),  36 (1/Tb^2 - 1/Ta^2);  .,  9 (1/Ta + 1/Tb)],   Ta = T_{j-1}, Tb = T_j,
+//        L_j = [168/Ta^3, 24/Ta^2;  -24/Ta^2, -3/Ta]  (couples node j to node j-1),   U_j = L_{j+1}^T,
+//
+// the same c as the reference's banded LU up to rounding (the 6M sequential pivots of trajectory.hpp:655-719 become M-1
+// sequential 2 x 2 block pivots; no pivoting is needed because S is SPD).  The back-propagation of CPU.hpp:97-161
+// (A^T lambda = dJ/dc, addPropCtoT, addPropCtoP) becomes: dJ/d(node states) = H(T_i)^T dJ/dc_i per piece (H = the
+// quintic Hermite map), one more solve S mu = dJ/dy with the SAME factors, and closed forms for the rest: with the
+// "adjoint quintic" ct_i = H(T_i)(0, mu_i, 0, mu_{i+1}),
+//        dJ/dq_j  = Pbar_j + crackle(ct_j) - crackle(ct_{j-1}),
+//        dJ/dT_i += -(P1bar.v_{i+1} + V1bar.a_{i+1} + A1bar.jerk_i(T_i))                      [dc/dT at fixed end states]
+//                   + jerk_c jerk_ct - snap_ct.a_{i+1} - snap_c.muA_{i+1} + crackle_ct.v_{i+1} + crackle_c.muV_{i+1}  at t = T_i.
+// Derivation and a numpy check against a dense restatement of the reference system: scripts/proto/reduced_minco.py.
+// =================================================================================================
+#define NODE_F 8  // doubles per node kept in bv.lu for K3: [0..2] inverse pivot block (i11, i12, i22), [3..6] G_j = L_j Di_{j-1}
+
+// K1 (fast) -----------------------------------------------------------------------------------------
+// One trajectory per CTA of two warps.  forwardT / splitToFineT / forwardP (CPU.hpp:626, :930, :729) by all threads, the
+// node blocks by one thread per node, the block LDL^T + forward substitution + back substitution by lanes 0..2 of
+// warp 0 (one right-hand side = one axis each; the 2 x 2 factorisation is recomputed by each of the three lanes instead
+// of being broadcast), the Hermite expansion to c by one thread per (piece, axis).
+// smem (doubles): Tc[coarseN+1] | Ts[M] | iT[M] | P[3(M+1)] | Y[6(M+1)] | nD[3M] | nL[4M] | nR[6M] | nG[4M] | wpi[3M ints]
+__global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
+    extern __shared__ double sm[];
+    const int b = bv.sub_traj0 + blockIdx.x;
+    if (bv.active && !bv.active[b]) return;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int p0 = bv.piece_off[b];
+    const int M = bv.piece_off[b + 1] - p0;
+    const int co0 = bv.coarse_off[b];
+    const int coarseN = bv.coarse_off[b + 1] - co0;
+    const DevParams par = bv.par[b];
+    const double* x = xin + bv.x_off[b];
+    const int dimT = bv.dimT[b];
+    double* Tc = sm;
+    double* Ts = Tc + coarseN + 1;
+    double* iT = Ts + M;
+    double* P = iT + M;
+    double* Y = P + 3 * (M + 1);
+    double* nD = Y + 6 * (M + 1);
+    double* nL = nD + 3 * M;
+    double* nR = nL + 4 * M;
+    double* nG = nR + 6 * M;
+    int* wpi = reinterpret_cast<int*>(nG + 4 * M);
+    PHASE_MARK(0, 0);
+
+    // waypoint index tables (free dimension, xi offset, vertex offset): one round trip instead of one per use
+    for (int i = tid; i < M - 1; i += 64) {
+        wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
+        wpi[M + i] = bv.wp_xi_off[p0 + i];
+        wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+    }
+    // head / tail states (column-major 3 x 3 [p v a] each): node 0 and node M
+    if (tid < 18) {
+        const double v = bv.headtail[18 * (size_t)b + tid];
+        const int e = tid < 9 ? tid : tid - 9, node = tid < 9 ? 0 : M;
+        if (e < 3)
+            P[3 * node + e] = v;
+        else
+            Y[6 * node + (e - 3)] = v;
+    }
+    // ---- forwardT (CPU.hpp:626-676) ----
+    if (par.softT) {
+        for (int i = tid; i < coarseN; i += 64) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+    } else if (tid == 0) {  // fixed total time: sequential sums as in the reference (rare path)
+        const int Ms1 = dimT;
+        for (int i = 0; i < Ms1; i++) Tc[i] = par.c2 ? c2_forward(x[i]) : exp(x[i]);
+        Tc[Ms1] = 0.0;
+        double s = 0.0;
+        for (int i = 0; i <= Ms1; i++) s += Tc[i];
+        const double den = 1.0 + s;
+        for (int i = 0; i <= Ms1; i++) Tc[i] /= den;
+        s = 0.0;
+        for (int i = 0; i <= Ms1; i++) s += Tc[i];
+        Tc[Ms1] = 1.0 - s;
+        for (int i = 0; i <= Ms1; i++) Tc[i] *= par.sumT;
+    }
+    __syncthreads();
+    // ---- splitToFineT (CPU.hpp:930-944) + forwardP (CPU.hpp:729-747) ----
+    for (int i = tid; i < M; i += 64) {
+        const int pl = bv.piece_poly[p0 + i];
+        const double Tv = Tc[pl] / bv.intervals[co0 + pl];
+        bv.T[p0 + i] = Tv;
+        Ts[i] = Tv;
+        iT[i] = 1.0 / Tv;
+    }
+    {   // four lanes per waypoint (sector-sized coalesced reads of xi and V, many loads in flight), one pass:
+        //   q = v0 + sc^2 * sum_a V_{a+1} xi_a^2,  sc = 2 / (1 + |xi|^2)
+        const int grp = tid >> 2, l4 = tid & 3;
+        const unsigned gmask = 0xFu << (lane & ~3);
+        for (int i = grp; i < M - 1; i += 16) {
+            const int k = wpi[i];
+            const double* V = bv.verts + 3 * (size_t)wpi[2 * M + i];
+            const double* xi = x + dimT + wpi[M + i];
+            double sn = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll 4
+            for (int a = l4; a < k; a += 4) {
+                const double xa = xi[a], x2 = xa * xa;
+                sn += x2;
+                sx += V[3 * (a + 1) + 0] * x2;
+                sy += V[3 * (a + 1) + 1] * x2;
+                sz += V[3 * (a + 1) + 2] * x2;
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                sn += __shfl_xor_sync(gmask, sn, o);
+                sx += __shfl_xor_sync(gmask, sx, o);
+                sy += __shfl_xor_sync(gmask, sy, o);
+                sz += __shfl_xor_sync(gmask, sz, o);
+            }
+            const double sc = 2.0 / (1.0 + sn), sc2 = sc * sc;
+            const double sd_ = l4 == 0 ? sx : (l4 == 1 ? sy : sz);
+            bv.wpw[4 * (size_t)(p0 + i) + l4] = (l4 == 3) ? sn : sd_;  // reused by addLayerPGrad in K3
+            if (l4 < 3) {
+                const double qd = V[l4] + sc2 * sd_;
+                bv.q[3 * (size_t)(p0 + i) + l4] = qd;
+                P[3 * (i + 1) + l4] = qd;
+            }
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(0, 1);
+
+    // ---- node blocks of S and the right-hand sides (one thread per node j = 1..M-1) ----
+    for (int j = 1 + tid; j < M; j += 64) {
+        const double ia = iT[j - 1], ib = iT[j];
+        const double ia2 = ia * ia, ib2 = ib * ib, ia3 = ia2 * ia, ib3 = ib2 * ib, ia4 = ia2 * ia2, ib4 = ib2 * ib2;
+        nD[3 * j + 0] = 192.0 * (ia3 + ib3);
+        nD[3 * j + 1] = 36.0 * (ib2 - ia2);
+        nD[3 * j + 2] = 9.0 * (ia + ib);
+        const double l11 = 168.0 * ia3, l12 = 24.0 * ia2, l21 = -24.0 * ia2, l22 = -3.0 * ia;
+        nL[4 * j + 0] = l11, nL[4 * j + 1] = l12, nL[4 * j + 2] = l21, nL[4 * j + 3] = l22;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double da = P[3 * j + d] - P[3 * (j - 1) + d], db = P[3 * (j + 1) + d] - P[3 * j + d];
+            double r0 = 360.0 * (da * ia4 + db * ib4);
+            double r1 = 60.0 * (db * ib3 - da * ia3);
+            if (j == 1) {  // known neighbour: head velocity / acceleration
+                const double hv = Y[d], ha = Y[3 + d];
+                r0 -= l11 * hv + l12 * ha;
+                r1 -= l21 * hv + l22 * ha;
+            }
+            if (j == M - 1) {  // known neighbour: tail velocity / acceleration through U_{M-1} = L_M^T with Ta := T_{M-1}
+                const double tv = Y[6 * M + d], ta = Y[6 * M + 3 + d];
+                r0 -= (168.0 * ib3) * tv + (-24.0 * ib2) * ta;
+                r1 -= (24.0 * ib2) * tv + (-3.0 * ib) * ta;
+            }
+            nR[6 * j + d] = r0;
+            nR[6 * j + 3 + d] = r1;
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(0, 2);
+
+    // ---- block LDL^T with the forward substitution fused in, then the back substitution: lanes 0..2 of warp 0 ----
+    double* fac = bv.lu + (size_t)NODE_F * p0;
+    if (warp == 0 && lane < 3 && M > 1) {
+        const int d = lane;
+        double d11 = nD[3], d12 = nD[4], d22 = nD[5];  // pivot block of node 1
+        double z0 = nR[6 + d], z1 = nR[9 + d];
+        // operands of the next node, loaded one step ahead of the dependent chain
+        double nl11 = 0, nl12 = 0, nl21 = 0, nl22 = 0, nd11 = 0, nd12 = 0, nd22 = 0, nr0 = 0, nr1 = 0;
+        if (M > 2) {
+            nl11 = nL[8], nl12 = nL[9], nl21 = nL[10], nl22 = nL[11];
+            nd11 = nD[6], nd12 = nD[7], nd22 = nD[8];
+            nr0 = nR[12 + d], nr1 = nR[15 + d];
+        }
+        for (int j = 1; j < M; j++) {
+            const double det = fma(d11, d22, -(d12 * d12));
+            const double id = fast_rcp(det);
+            const double i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;  // inverse pivot block
+            const double w0 = i11 * z0 + i12 * z1, w1 = i12 * z0 + i22 * z1;  // w_j = Di_j z_j
+            nR[6 * j + d] = w0;
+            nR[6 * j + 3 + d] = w1;
+            if (d == 0) fac[NODE_F * j + 0] = i11, fac[NODE_F * j + 1] = i12, fac[NODE_F * j + 2] = i22;
+            if (j + 1 < M) {
+                const double l11 = nl11, l12 = nl12, l21 = nl21, l22 = nl22;
+                const double c11 = nd11, c12 = nd12, c22 = nd22, r0 = nr0, r1 = nr1;
+                if (j + 2 < M) {
+                    const int q = j + 2;
+                    nl11 = nL[4 * q], nl12 = nL[4 * q + 1], nl21 = nL[4 * q + 2], nl22 = nL[4 * q + 3];
+                    nd11 = nD[3 * q], nd12 = nD[3 * q + 1], nd22 = nD[3 * q + 2];
+                    nr0 = nR[6 * q + d], nr1 = nR[6 * q + 3 + d];
+                }
+                const double g11 = l11 * i11 + l12 * i12, g12 = l11 * i12 + l12 * i22;  // G_{j+1} = L_{j+1} Di_j
+                const double g21 = l21 * i11 + l22 * i12, g22 = l21 * i12 + l22 * i22;
+                d11 = c11 - (g11 * l11 + g12 * l12);  // D_{j+1} - G L^T
+                d12 = c12 - (g11 * l21 + g12 * l22);
+                d22 = c22 - (g21 * l21 + g22 * l22);
+                z0 = r0 - (l11 * w0 + l12 * w1);  // r_{j+1} - L_{j+1} w_j
+                z1 = r1 - (l21 * w0 + l22 * w1);
+                if (d == 0) {
+                    double* gs = nG + 4 * (j + 1);
+                    gs[0] = g11, gs[1] = g12, gs[2] = g21, gs[3] = g22;
+                    double* gg = fac + NODE_F * (j + 1) + 3;
+                    gg[0] = g11, gg[1] = g12, gg[2] = g21, gg[3] = g22;
+                }
+            }
+        }
+        __syncwarp(0x7u);
+        PHASE_MARK(0, 3);
+        // y_j = w_j - G_{j+1}^T y_{j+1}
+        double y0 = nR[6 * (M - 1) + d], y1 = nR[6 * (M - 1) + 3 + d];
+        Y[6 * (M - 1) + d] = y0;
+        Y[6 * (M - 1) + 3 + d] = y1;
+        for (int j = M - 2; j >= 1; j--) {
+            const double* g = nG + 4 * (j + 1);
+            const double t0 = nR[6 * j + d] - (g[0] * y0 + g[2] * y1);
+            const double t1 = nR[6 * j + 3 + d] - (g[1] * y0 + g[3] * y1);
+            y0 = t0, y1 = t1;
+            Y[6 * j + d] = y0;
+            Y[6 * j + 3 + d] = y1;
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(0, 4);
+
+    // ---- Hermite expansion: c_i from the end states of piece i, one thread per (piece, axis) ----
+    for (int task = tid; task < 3 * M; task += 64) {
+        const int i = task / 3, d = task - 3 * i;
+        const double t1 = iT[i], t2 = t1 * t1, t3 = t2 * t1, t4 = t2 * t2, t5 = t4 * t1;
+        const double P0 = P[3 * i + d], P1 = P[3 * i + 3 + d];
+        const double V0 = Y[6 * i + d], A0 = Y[6 * i + 3 + d], V1 = Y[6 * i + 6 + d], A1 = Y[6 * i + 9 + d];
+        const double dP = P1 - P0;
+        const double c3 = (10.0 * dP) * t3 - (4.0 * V1 + 6.0 * V0) * t2 - (3.0 * A0 - A1) * (0.5 * t1);
+        const double c4 = (-15.0 * dP) * t4 + (7.0 * V1 + 8.0 * V0) * t3 + (3.0 * A0 - 2.0 * A1) * (0.5 * t2);
+        const double c5 = (6.0 * dP) * t5 - (3.0 * (V1 + V0)) * t4 + (A1 - A0) * (0.5 * t3);
+        double* cg = bv.c + 18 * (size_t)(p0 + i) + d;
+        cg[0] = P0, cg[3] = V0, cg[6] = 0.5 * A0, cg[9] = c3, cg[12] = c4, cg[15] = c5;
+    }
+    PHASE_MARK(0, 5);
+}
+
+// K3 (fast) -----------------------------------------------------------------------------------------
+// One trajectory per CTA of two warps: Hermite adjoint per piece, the node right-hand sides, the two substitution sweeps
+// with K1's factors (lanes 0..2 of warp 0, a chain of two FMAs per node) while warp 1 sums the cost in the reference's
+// order, the closed-form dJ/dT and dJ/dq, then mergeToCoarseGradT / addLayerTGrad / addLayerPGrad (CPU.hpp:946, :816, :897).
+// smem (doubles): Ts[M] | iT[M] | sp[9M] | ep[9M] | fc[8M] | Z[6M] | kt[3M] | gTd[M] | gT[M] | gq[3M] | gTc[coarseN+1] |
+//                 em[2M] | tfac[coarseN] | ivs, ioff [coarseN ints each] | wpi[3M ints]
+__global__ void __launch_bounds__(64)
+    minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
+                          double* __restrict__ grad_out) {
+    extern __shared__ double sm[];
+    const int b = bv.sub_traj0 + blockIdx.x;
+    if (bv.active && !bv.active[b]) return;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int p0 = bv.piece_off[b];
+    const int M = bv.piece_off[b + 1] - p0;
+    const int co0 = bv.coarse_off[b];
+    const int coarseN = bv.coarse_off[b + 1] - co0;
+    const DevParams par = bv.par[b];
+    const double* x = xin + bv.x_off[b];
+    double* grad = grad_out + bv.x_off[b];
+    const int dimT = bv.dimT[b];
+    const int nx = bv.x_off[b + 1] - bv.x_off[b];
+    double* Ts = sm;
+    double* iT = Ts + M;
+    double* sp = iT + M;
+    double* ep = sp + 9 * (size_t)M;
+    double* fc = ep + 9 * (size_t)M;
+    double* Z = fc + NODE_F * (size_t)M;
+    double* kt = Z + 6 * (size_t)M;
+    double* gTd = kt + 3 * (size_t)M;
+    double* gT = gTd + M;
+    double* gq = gT + M;
+    double* gTc = gq + 3 * (size_t)M;
+    double* em = gTc + coarseN + 1;
+    double* tfac = em + 2 * (size_t)M;
+    int* ivs = reinterpret_cast<int*>(tfac + coarseN);
+    int* ioff = ivs + coarseN;
+    int* wpi = ioff + coarseN;
+    PHASE_MARK(2, 0);
+
+    const double* cg_ = bv.c + 18 * (size_t)p0;
+    const double* gd_ = bv.gdC + 18 * (size_t)p0;
+    const double* tailst = bv.headtail + 18 * (size_t)b + 9;  // tail p (0..2), v (3..5), a (6..8)
+    // K1's factors -> shared memory, asynchronously (8 doubles per node)
+    {
+        const double* fg = bv.lu + (size_t)NODE_F * p0;
+        for (int e = tid; e < NODE_F * M / 2; e += 64) cp_async16(fc + 2 * e, fg + 2 * e);
+        cp_async_commit();
+    }
+    // ---- Hermite adjoint per piece: (P0b, V0b, A0b | P1b, V1b, A1b) = H(T_i)^T dJ/dc_i, and dc/dT at fixed end states ----
+    for (int i = tid; i < M; i += 64) {
+        const double t = bv.T[p0 + i];
+        const double i1 = 1.0 / t, i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2, i5 = i4 * i1;
+        Ts[i] = t, iT[i] = i1;
+        const double* ci = cg_ + 18 * (size_t)i;
+        const double* gi = gd_ + 18 * (size_t)i;
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double g0 = gi[d], g1 = gi[3 + d], g2 = gi[6 + d], g3 = gi[9 + d], g4 = gi[12 + d], g5 = gi[15 + d];
+            const double dP = (10.0 * i3) * g3 - (15.0 * i4) * g4 + (6.0 * i5) * g5;
+            const double V0b = g1 - (6.0 * i2) * g3 + (8.0 * i3) * g4 - (3.0 * i4) * g5;
+            const double V1b = (7.0 * i3) * g4 - (4.0 * i2) * g3 - (3.0 * i4) * g5;
+            const double A0b = 0.5 * g2 - (1.5 * i1) * g3 + (1.5 * i2) * g4 - (0.5 * i3) * g5;
+            const double A1b = (0.5 * i1) * g3 - i2 * g4 + (0.5 * i3) * g5;
+            sp[9 * i + d] = g0 - dP, sp[9 * i + 3 + d] = V0b, sp[9 * i + 6 + d] = A0b;
+            ep[9 * i + d] = dP, ep[9 * i + 3 + d] = V1b, ep[9 * i + 6 + d] = A1b;
+            const double V1 = (i + 1 < M) ? ci[18 + 3 + d] : tailst[3 + d];
+            const double A1 = (i + 1 < M) ? 2.0 * ci[18 + 6 + d] : tailst[6 + d];
+            const double J1 = 6.0 * ci[9 + d] + (24.0 * t) * ci[12 + d] + (60.0 * t * t) * ci[15 + d];
+            s -= dP * V1 + V1b * A1 + A1b * J1;
+        }
+        gTd[i] = s;
+    }
+    if (warp == 1) {
+        for (int i = lane; i < M - 1; i += 32) {
+            wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
+            wpi[M + i] = bv.wp_xi_off[p0 + i];
+            wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+        }
+    }
+    __syncthreads();
+    // ---- node right-hand sides: dJ/dy_j = end part of piece j-1 + start part of piece j ----
+    for (int e = tid; e < 6 * (M - 1); e += 64) {
+        const int j = 1 + e / 6, r = e - 6 * (j - 1);  // r = 0..2: velocity, 3..5: acceleration
+        Z[6 * j + r] = ep[9 * (j - 1) + 3 + r] + sp[9 * j + 3 + r];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    PHASE_MARK(2, 1);
+    if (warp == 0) {
+        // ---- S mu = dJ/dy with K1's factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
+        if (lane < 3 && M > 1) {
+            const int d = lane;
+            double z0 = Z[6 + d], z1 = Z[9 + d];
+            {
+                const double* f = fc + NODE_F;
+                Z[6 + d] = f[0] * z0 + f[1] * z1;
+                Z[9 + d] = f[1] * z0 + f[2] * z1;
+            }
+            for (int j = 2; j < M; j++) {
+                const double* f = fc + NODE_F * j;
+                const double t0 = Z[6 * j + d] - (f[3] * z0 + f[4] * z1);
+                const double t1 = Z[6 * j + 3 + d] - (f[5] * z0 + f[6] * z1);
+                z0 = t0, z1 = t1;
+                Z[6 * j + d] = f[0] * z0 + f[1] * z1;
+                Z[6 * j + 3 + d] = f[1] * z0 + f[2] * z1;
+            }
+            double m0 = Z[6 * (M - 1) + d], m1 = Z[6 * (M - 1) + 3 + d];
+            for (int j = M - 2; j >= 1; j--) {
+                const double* g = fc + NODE_F * (j + 1) + 3;
+                const double t0 = Z[6 * j + d] - (g[0] * m0 + g[2] * m1);
+                const double t1 = Z[6 * j + 3 + d] - (g[1] * m0 + g[3] * m1);
+                m0 = t0, m1 = t1;
+                Z[6 * j + d] = m0;
+                Z[6 * j + 3 + d] = m1;
+            }
+        }
+    } else {
+        // ---- meanwhile: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988), time-map derivative, tables ----
+        for (int i = lane; i < M; i += 32) {
+            em[i] = bv.energy[p0 + i];
+            em[M + i] = bv.pen[p0 + i];
+        }
+        for (int i = lane; i < coarseN; i += 32) ivs[i] = bv.intervals[co0 + i];
+        if (par.softT) {
+            for (int i = lane; i < coarseN; i += 32) {  // time map and its derivative (CPU.hpp:639-641, 830-838)
+                const double t = x[i];
+                double Tv, dv;
+                if (par.c2) {
+                    Tv = c2_forward(t);
+                    if (t > 0)
+                        dv = t + 1.0;
+                    else {
+                        const double den = (0.5 * t - 1.0) * t + 1.0;
+                        dv = (1.0 - t) / (den * den);
+                    }
+                } else {
+                    Tv = exp(t);
+                    dv = Tv;
+                }
+                gTc[i] = Tv;
+                tfac[i] = dv;
+            }
+        }
+        __syncwarp();
+        double part = 0.0;
+        if (lane == 0) {
+            for (int i = 0; i < M; i++) part += em[i];
+        } else if (lane == 1) {
+            for (int i = 0; i < M; i++) part += em[M + i];
+        } else if (lane == 2) {
+            if (par.softT) {
+                for (int i = 0; i < coarseN; i++) part += gTc[i];
+            } else {
+                for (int i = 0; i < M; i++) part += Ts[i];  // fixed total time: rho = 0 anyway
+            }
+        } else if (lane == 3) {
+            int o = 0;
+            for (int i = 0; i < coarseN; i++) {
+                ioff[i] = o;
+                o += ivs[i];
+            }
+        }
+        const double pn = __shfl_sync(0xffffffffu, part, 1), sT = __shfl_sync(0xffffffffu, part, 2);
+        if (lane == 0) cost_out[b] = (part + pn) + par.rho * sT;
+        // pull x and the vertex range of this trajectory towards L2 for addLayerPGrad
+        for (int o = lane * 16; o < nx; o += 32 * 16) prefetch_l2(x + o);
+        if (M > 1) {
+            const double* v0 = bv.verts + 3 * (size_t)bv.wp_vert_off[p0];
+            const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
+            for (const double* q = v0 + lane * 16; q < v1; q += 32 * 16) prefetch_l2(q);
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(2, 4);
+    // ---- dJ/dT (energy + penalty partial from K2, the two closed forms above, rho of CPU.hpp:989) and crackle(ct) ----
+    for (int i = tid; i < M; i += 64) {
+        const double t = Ts[i], i1 = iT[i], i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2;
+        const double* ci = cg_ + 18 * (size_t)i;
+        double s = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double mV0 = (i > 0) ? Z[6 * i + d] : 0.0, mA0 = (i > 0) ? Z[6 * i + 3 + d] : 0.0;
+            const double mV1 = (i + 1 < M) ? Z[6 * i + 6 + d] : 0.0, mA1 = (i + 1 < M) ? Z[6 * i + 9 + d] : 0.0;
+            const double ct3 = -((4.0 * mV1 + 6.0 * mV0) * i2) - (3.0 * mA0 - mA1) * (0.5 * i1);
+            const double ct4 = (7.0 * mV1 + 8.0 * mV0) * i3 + (3.0 * mA0 - 2.0 * mA1) * (0.5 * i2);
+            const double ct5 = (mA1 - mA0) * (0.5 * i3) - (3.0 * (mV1 + mV0)) * i4;
+            const double c3 = ci[9 + d], c4 = ci[12 + d], c5 = ci[15 + d];
+            const double jc = 6.0 * c3 + (24.0 * t) * c4 + (60.0 * t * t) * c5;
+            const double sc = 24.0 * c4 + (120.0 * t) * c5;
+            const double kc = 120.0 * c5;
+            const double jt = 6.0 * ct3 + (24.0 * t) * ct4 + (60.0 * t * t) * ct5;
+            const double st = 24.0 * ct4 + (120.0 * t) * ct5;
+            const double ktv = 120.0 * ct5;
+            const double V1 = (i + 1 < M) ? ci[18 + 3 + d] : tailst[3 + d];
+            const double A1 = (i + 1 < M) ? 2.0 * ci[18 + 6 + d] : tailst[6 + d];
+            s += jc * jt - st * A1 - sc * mA1 + ktv * V1 + kc * mV1;
+            kt[3 * i + d] = ktv;
+        }
+        gT[i] = bv.gdT[p0 + i] + (gTd[i] + s) + par.rho;
+    }
+    __syncthreads();
+    // ---- dJ/dq (addPropCtoP): waypoint w = node w+1 ----
+    for (int e = tid; e < 3 * (M - 1); e += 64) {
+        const int w = e / 3, d = e - 3 * w;
+        gq[e] = (ep[9 * w + d] + sp[9 * (w + 1) + d]) + (kt[3 * (w + 1) + d] - kt[3 * w + d]);
+    }
+    __syncthreads();
+    PHASE_MARK(2, 5);
+    // ---- mergeToCoarseGradT (CPU.hpp:946-959): mean over the pieces of each polytope; one thread per polytope ----
+    for (int i = tid; i < coarseN; i += 64) {
+        const int iv = ivs[i], offset = ioff[i];
+        double sgt = 0.0;
+        for (int a = 0; a < iv; a++) sgt += gT[offset + a];
+        const double gm = sgt / iv;
+        // ---- addLayerTGrad (CPU.hpp:816-894), free total time: the factor was computed above ----
+        if (par.softT) {
+            if (i < dimT) grad[i] = gm * tfac[i];
+        } else
+            gTc[i] = gm;
+    }
+    if (!par.softT) {
+        __syncthreads();
+        if (tid == 0) {
+            const int Ms1 = dimT;
+            const double gTail = par.sumT * gTc[Ms1];
+            double expTauSum = 0.0, gFreeDotExpTau = 0.0;
+            for (int i = 0; i < Ms1; i++) {
+                const double t = x[i];
+                const double gFree = par.sumT * gTc[i];
+                double eTau;
+                if (par.c2) {
+                    if (t > 0)
+                        eTau = (0.5 * t + 1.0) * t + 1.0;
+                    else
+                        eTau = 1.0 / ((0.5 * t - 1.0) * t + 1.0);
+                } else
+                    eTau = exp(t);
+                expTauSum += eTau;
+                gFreeDotExpTau += eTau * gFree;
+            }
+            const double den = expTauSum + 1.0;
+            for (int i = 0; i < Ms1; i++) {
+                const double t = x[i];
+                const double gFree = par.sumT * gTc[i];
+                double dE;
+                if (par.c2) {
+                    if (t > 0)
+                        dE = t + 1.0;
+                    else {
+                        const double ds = (0.5 * t - 1.0) * t + 1.0;
+                        dE = (1.0 - t) / (ds * ds);
+                    }
+                } else
+                    dE = exp(t);
+                grad[i] = (gFree - gTail) * dE / den - (gFreeDotExpTau - gTail * expTauSum) * dE / (den * den);
+            }
+        }
+    }
+    PHASE_MARK(2, 6);
+    // ---- addLayerPGrad (CPU.hpp:897-928) ----
     {   // four lanes per waypoint, ONE streaming pass: with s_a = V_{a+1}.gq, q1 = 1 + |xi|^2 and W = sum_a V_{a+1} xi_a^2
         // (both stored by K1):  gd_a = 4 s_a xi_a / q1,  gdot = 4 (W.gq) / q1,  d/dxi_a = xi_a (8 s_a / q1^2 - 16 (W.gq) / q1^3)
         const int grp = tid >> 2, l4 = tid & 3;
@@ -1579,13 +1847,14 @@ __global__ void __launch_bounds__(64)
             }
         }
     }
-#endif
     PHASE_MARK(2, 7);
 }
+#endif  // !FRX_EXACT (reduced-system kernels)
 
 // ------------------------------------------------------------------------------------------------
 // Host-side launchers
 // ------------------------------------------------------------------------------------------------
+#ifdef FRX_EXACT
 size_t forward_smem_bytes(int M, int coarseN) {
     const size_t ust = (size_t)6 * M * UST, tc = (size_t)coarseN + 1;
     return sizeof(double) * ((size_t)RING * BW + 32 + (ust > tc ? ust : tc));
@@ -1594,6 +1863,14 @@ size_t backward_smem_bytes(int M, int coarseN) {
     return sizeof(double) * ((size_t)NBLK * BLKD + (size_t)18 * M + (size_t)4 * M + coarseN + 1 + (size_t)2 * M + coarseN + (coarseN + 1) + 1 +
                              (3 * (size_t)M + 1) / 2 + 2);
 }
+#else
+size_t forward_smem_bytes(int M, int coarseN) {  // see the layout comment of minco_forward_kernel
+    return sizeof(double) * ((size_t)coarseN + 1 + (size_t)28 * M + 9 + (3 * (size_t)M + 1) / 2 + 2);
+}
+size_t backward_smem_bytes(int M, int coarseN) {  // see the layout comment of minco_backward_kernel
+    return sizeof(double) * ((size_t)44 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 2);
+}
+#endif
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {
     PenaltyLaunch pl;
@@ -1620,14 +1897,26 @@ PenaltyLaunch plan_penalty(const BatchView& bv) {
     return pl;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and per device, and every launch must request no more than
+// the current value: batches of different shapes coexist (frx.h: distinct batches are independent), so the limit only
+// ever grows, under a lock (two threads may create batches concurrently).
 cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem) {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(minco_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem);
+    static std::mutex mu;
+    static size_t cur[64][3];  // [device][kernel], zero-initialised
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(minco_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(penalty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pen_smem);
-    return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t want[3] = {fwd_smem, bwd_smem, pen_smem};
+    const void* fn[3] = {(const void*)minco_forward_kernel, (const void*)minco_backward_kernel, (const void*)penalty_kernel};
+    for (int k = 0; k < 3; k++) {
+        if (want[k] <= cur[dev][k]) continue;
+        e = cudaFuncSetAttribute(fn[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want[k]);
+        if (e != cudaSuccess) return e;
+        cur[dev][k] = want[k];
+    }
+    return cudaSuccess;
 }
 
 static void launch_penalty(const BatchView& bv, const PenaltyLaunch& pl, cudaStream_t st) {

@@ -624,9 +624,13 @@ __global__ void argmin_kernel(const double* __restrict__ cost, int B, int* out_i
     }
 }
 
-__global__ void gather_fx_kernel(const TrajSolve* st, int B, double* out) {
+// Penalised objective AT the returned iterate: solver_run's last forward pass evaluates every trajectory at its final x
+// into sv.cost.  (TrajSolve::fx is lbfgs.hpp's *ptr_fx: after a failed line search or a tick cut-off it still holds the
+// rejected trial's value while x was reverted to xp — the reference discards it, CPU.hpp:1249; ranking candidates on it
+// would compare costs that do not belong to the trajectories returned.)
+__global__ void gather_fx_kernel(const double* __restrict__ cost, int B, double* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) out[i] = st[i].fx;
+    if (i < B) out[i] = cost[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -727,6 +731,10 @@ int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, const EvalFn& 
     if (r != FRX_OK) return r;
     SolverView& sv = s->sv;
     solver_bind_active(bv, s, true);
+    struct Unbind {  // bv.active must be nullptr again on EVERY exit: a stale mask would make later evaluations skip trajectories
+        BatchView& bv;
+        ~Unbind() { bv.active = nullptr; }
+    } unbind{bv};
     int ticks = 0, n_active = bv.B;
     // Measurement: the first update launch of every poll group is bracketed by events and counts the history bytes it
     // streams (-> achieved HBM bandwidth of the direction update, bench.py "solves.update_kernel").
@@ -821,12 +829,12 @@ int solver_poll_active(SolverState* s, cudaStream_t st, int* n_active) {
 
 int solver_fetch(SolverState* s, double* final_cost, int* status, int* iters, int* evals, double* x_final) {
     SolverView& sv = s->sv;
-    gather_fx_kernel<<<(sv.B + 255) / 256, 256>>>(sv.st, sv.B, s->fx_dev);
+    gather_fx_kernel<<<(sv.B + 255) / 256, 256>>>(sv.cost, sv.B, s->fx_dev);
     if (cudaDeviceSynchronize() != cudaSuccess) return FRX_ERR_CUDA;
     std::vector<TrajSolve> h(sv.B);
     if (cudaMemcpy(h.data(), sv.st, sizeof(TrajSolve) * sv.B, cudaMemcpyDeviceToHost) != cudaSuccess) return FRX_ERR_CUDA;
+    if (final_cost && cudaMemcpy(final_cost, s->fx_dev, sizeof(double) * sv.B, cudaMemcpyDeviceToHost) != cudaSuccess) return FRX_ERR_CUDA;
     for (int i = 0; i < sv.B; i++) {
-        if (final_cost) final_cost[i] = h[i].fx;
         if (status) status[i] = (h[i].phase == PH_DONE) ? h[i].status : LBFGSERR_MAXIMUMITERATION;
         if (iters) iters[i] = h[i].k;
         if (evals) evals[i] = h[i].n_evals;

@@ -60,6 +60,7 @@ def lib():
         L.fro_time_solves_mt.restype = cd
         L.fro_time_solves_mt.argtypes = [P(vp), ci, cd, ci, P(cd), P(ci), P(ci), P(ci)]
         L.fro_brute_force_vertices.argtypes = [P(cd), ci, P(cd), ci]
+        L.fro_vpolys.argtypes = [vp, P(ci), P(cd)]
         L.fro_banded_solve.argtypes = [P(cd), ci, P(cd), ci]
         L.fro_lbfgs_testfn.argtypes = [ci, ci, P(cd), P(cd), ci, ci, cd, cd, ci, P(ci), P(ci)]
         L.fro_testfn_eval.restype = cd
@@ -169,6 +170,18 @@ def brute_force_vertices(faces):
     out = np.zeros(3 * 1024)
     v = L.fro_brute_force_vertices(_dp(f), len(f) // 6, _dp(out), 1024)
     return out[: 3 * v].reshape(v, 3).copy()
+
+
+def vpolys(problem):
+    """V-polytopes of a corridor by the oracle's own brute-force enumeration (no product code involved)."""
+    L = lib()
+    s = problem.as_struct()
+    off = np.zeros(2 * problem.n_poly, np.int32)
+    if L.fro_vpolys(C.cast(C.pointer(s), C.c_void_p), _ip(off), None) != 0:
+        raise RuntimeError("oracle: empty polytope or intersection")
+    verts = np.zeros(3 * int(off[-1]))
+    L.fro_vpolys(C.cast(C.pointer(s), C.c_void_p), _ip(off), _dp(verts))
+    return off, verts
 
 
 def ref_lbfgs():

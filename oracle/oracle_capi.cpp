@@ -3,6 +3,7 @@
 // ABI (include/frx.h is included only for the argument structs), but REQUIRES the V-polytopes to
 // be supplied (the tests pass the product's, after checking them against brute_force_vertices).
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -169,6 +170,39 @@ int fro_brute_force_vertices(const double* faces, int F, double* out, int cap) {
         out[3 * i] = v[3 * i], out[3 * i + 1] = v[3 * i + 1], out[3 * i + 2] = v[3 * i + 2];
     }
     return V;
+}
+
+// V-polytopes of a corridor by the oracle's own brute-force enumeration, in the layout SE3GCOPTER::extractVs builds
+// (CPU.hpp:1031-1074: polytope i at slot 2i, the intersection of i and i+1 at slot 2i+1, "origin + edges" columns): lets
+// bench.py's reference arm run without the product library.  Vertex ORDER is the enumeration's, not quickhull's.
+// Two calls: verts == nullptr fills off[2*n_poly]; then verts[3*off[2*n_poly-1]].  Returns 0, or -2 on an empty polytope.
+int fro_vpolys(const frx_problem* p, int* off, double* verts) {
+    const int nv = 2 * p->n_poly - 1;
+    off[0] = 0;
+    for (int k = 0; k < nv; k++) {
+        const int i = k / 2;
+        std::vector<double> f;
+        auto add = [&](int poly) {
+            for (int a = p->face_off[poly]; a < p->face_off[poly + 1]; a++) {
+                const double* src = p->faces + 6 * (size_t)a;
+                const double nn = std::sqrt(src[0] * src[0] + src[1] * src[1] + src[2] * src[2]);
+                for (int q = 0; q < 3; q++) f.push_back(src[q] / nn);  // normals normalised as CPU.hpp:1116
+                for (int q = 3; q < 6; q++) f.push_back(src[q]);
+            }
+        };
+        add(i);
+        if (k & 1) add(i + 1);
+        auto v = brute_force_vertices(f.data(), (int)f.size() / 6);
+        const int V = (int)v.size() / 3;
+        if (V < 4) return -2;
+        if (verts) {
+            double* dst = verts + 3 * (size_t)off[k];
+            for (int c = 0; c < V; c++)
+                for (int q = 0; q < 3; q++) dst[3 * c + q] = c == 0 ? v[q] : v[3 * c + q] - v[q];
+        }
+        off[k + 1] = off[k] + V;
+    }
+    return 0;
 }
 
 // ---- stand-alone pieces for unit tests -------------------------------------------------------

@@ -15,12 +15,11 @@ out = (C.c_longlong * 96)()
 b.lib.frx_debug_phase_clocks.argtypes = [C.POINTER(C.c_longlong)]
 b.lib.frx_debug_phase_clocks(out)
 v = np.array(out[:], dtype=np.int64)
-names = {0: ["start", "fwdT/P done", "ring prologue", "pivot loop", "retire last", "back subst"],
-         2: ["start", "prologue", "sync", "sweep 1", "sweep 2(+transition)", "propCtoT", "merge+layerT", "layerP"]}
-print("K1 pair loop (warp 0, lane 0, sums over all pairs): loads+sync %d | step A incl. 1/u11 %d | step B to va %d | whole pair %d" % tuple(v[10:14]))
+names = {0: ["start", "forwardT/P", "node blocks", "block LDL^T + fwd subst", "back subst (+sync)", "Hermite -> c"],
+         2: ["start", "Hermite adjoint + rhs", "-", "-", "substitution sweeps / cost", "dJ/dT, dJ/dq", "merge+layerT", "layerP"]}
 for k in (0, 2):
     for w in (0, 1):
-        m = v[k*32 + w*16: k*32 + w*16 + len(names[k])]
-        d = np.diff(m)
-        if k == 0: print(f"K1 warp {w}: phase loop work {v[k*32 + w*16 + 8]} cyc, barrier wait {v[k*32 + w*16 + 9]} cyc")
-        print(f"K{k+1} warp {w}: total {m[-1]-m[0] if m[-1] else 0} cyc | " + " | ".join(f"{n} {x}" for n, x in zip(names[k][1:], d)))
+        m = v[k*32 + w*16: k*32 + w*16 + len(names[k])].astype(np.int64)
+        idx = [i for i in range(len(m)) if m[i] != 0]
+        parts = [f"{names[k][j]} {m[j] - m[i]}" for i, j in zip(idx[:-1], idx[1:])]
+        print(f"K{k+1} warp {w}: total {m[idx[-1]] - m[idx[0]] if idx else 0} cyc | " + " | ".join(parts))

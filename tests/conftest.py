@@ -15,9 +15,16 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Build libfrx.so and the oracle once per session (no-op when up to date)."""
+    import shutil
+    import subprocess
+
     import __graft_entry__ as ge
 
-    ge.build()
+    have_nvcc = os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or shutil.which("nvcc")
+    if have_nvcc or os.path.exists(os.path.join(ROOT, "fast_racing_b200", "libfrx.so")):
+        ge.build()
+    else:  # CPU-only checkout without the CUDA toolkit: the oracle tier still runs; tests that need libfrx.so fail loudly
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
 
 
 @pytest.fixture(scope="session")

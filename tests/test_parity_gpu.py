@@ -122,6 +122,28 @@ def test_capacity_limit_is_reported():
     assert e.value.status == api.FRX_ERR_CAPACITY
 
 
+def test_batches_of_different_shapes_coexist(oracle_mod):
+    """Distinct batches are independent (frx.h): creating a SMALLER batch must not break a live larger one (the
+    per-function dynamic shared-memory limit is process-global and may only grow)."""
+    big = [synth.make_problem(95, 120, np.full(120, 30), 64)]
+    small = [synth.make_problem(96, 3, 6, 4)]
+    bb = api.Batch(big)
+    xb = bb.initial_guess() + 0.1 * np.random.default_rng(5).normal(size=bb.total_x)
+    c0, g0 = bb.eval(xb)
+    bs = api.Batch(small)
+    cs, _ = bs.eval(bs.initial_guess())
+    c1, g1 = bb.eval(xb)  # the larger batch, after the smaller one configured the kernels
+    assert np.isfinite(cs).all() and np.isfinite(c1).all()
+    assert np.array_equal(c0, c1) and np.array_equal(g0, g1)
+    off, verts = bb.vpolys(0)
+    o = oracle_mod.Oracle(big[0].with_vpolys(off, verts))
+    f, g = o.eval(xb)
+    assert abs(c1[0] - f) <= COST_RTOL * abs(f) and rel_err(g1, g) <= GRAD_RTOL
+    o.close()
+    bs.close()
+    bb.close()
+
+
 def test_eval_parity_time_maps(oracle_mod):
     """Fixed total time (rho = 0) with the C2 and the exp diffeomorphism; soft time with exp."""
     p = synth.make_problem(41, 6, 10, 8)
@@ -227,19 +249,23 @@ def test_solver_converged_cost_matches_oracle(oracle_mod):
     r = batch.optimize(tol)
     x0 = batch.initial_guess()
     n_converged = 0
+    # statuses of a run that went as far as the arithmetic allows: the delta / gradient stops, or a line search that can
+    # no longer resolve a decrease below the rounding noise of f (delta = 1e-13 is 7 orders tighter than the reference's)
+    rounding_exits = (-1005, -1001, -1003, -1007, -1008)  # MAXIMUMLINESEARCH, INCREASEGRADIENT, WIDTHTOOSMALL, MINIMUMSTEP, ROUNDING_ERROR
     for i, o in _oracles(oracle_mod, batch, probs):
         p0, p1 = batch.x_off[i], batch.x_off[i + 1]
         f, _ = o.eval(r["x"][p0:p1])  # oracle cost at the GPU's final iterate
+        lo, hi = _oracle_band(oracle_mod, o, tol)
+        # north_star: converged costs within 1e-6 relative of the reference's — for EVERY trajectory, whatever the exit
+        assert lo * (1 - 1e-6) <= f <= hi * (1 + 1e-6), (i, int(r["status"][i]), f, lo, hi)
         if r["status"][i] >= 0:
             assert abs(f - r["final_cost"][i]) <= 1e-10 * f
-            lo, hi = _oracle_band(oracle_mod, o, tol)
-            assert lo * (1 - 1e-6) <= f <= hi * (1 + 1e-6), (i, f, lo, hi)
             n_converged += 1
         else:
             # A line search can fail on some rounding paths (the reference's own lbfgs_optimize, fed these evaluations,
             # returns the same error codes; SE3GCOPTER::optimize swallows them, CPU.hpp:1249): the iterate returned is
-            # then the last accepted one, a descent from the start, while the returned cost is the last TRIAL's as in
-            # lbfgs.hpp:1291-1298 + 1439).  Bit-identical paths are the reference-order tests.
+            # then the last accepted one.  Bit-identical paths are the reference-order tests.
+            assert int(r["status"][i]) in rounding_exits, (i, r["status"][i])
             assert f < o.eval(x0[p0:p1])[0], (i, r["status"][i])
         # output trajectory: durations / coefficients / jerk cost consistent with the oracle at that x
         T, q, c = o.forward(r["x"][p0:p1])
@@ -248,7 +274,7 @@ def test_solver_converged_cost_matches_oracle(oracle_mod):
         co = r["coeffs"][18 * a0:18 * a1].reshape(-1, 6, 3)  # [piece][col][dim], highest order first
         assert rel_err(co[:, ::-1, :].reshape(-1), c) <= 1e-10
         assert np.isfinite(r["jerk_cost"][i]) and 0 < r["jerk_cost"][i] < f
-    assert n_converged >= len(probs) // 2, r["status"]
+    assert n_converged >= 1, r["status"]
     bi, bc = batch.argmin()
     assert bi == int(np.argmin(r["final_cost"])) and bc == r["final_cost"].min()
     batch.close()
