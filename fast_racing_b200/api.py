@@ -161,6 +161,8 @@ def load_library():
         "frx_batch_profile_eval": (ci, [vp, vp, vp, vp, vp, ci, P(cd)]),
         "frx_batch_penalty_launch": (ci, [vp, P(C.c_longlong)]),
         "frx_measure_fp64_tflops": (cd, []),
+        "frx_device_numa_node": (ci, [ci]),
+        "frx_bind_thread_to_device": (ci, [ci]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -174,7 +176,7 @@ EXPORTED_SYMBOLS = [
     "frx_batch_create", "frx_batch_destroy", "frx_batch_count", "frx_batch_dims", "frx_batch_x_offsets",
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
     "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_batch_set_reference_order", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
-    "frx_batch_last_ms", "frx_strerror", "frx_version",
+    "frx_batch_last_ms", "frx_strerror", "frx_version", "frx_device_numa_node", "frx_bind_thread_to_device",
 ]
 
 

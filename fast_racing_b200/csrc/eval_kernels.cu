@@ -114,6 +114,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// One bulk (TMA-unit) prefetch of a whole byte range into L2: the 16-byte aligned interior of [p, p + bytes).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
+    const unsigned long long a = ((unsigned long long)p + 15ull) & ~15ull, e = ((unsigned long long)p + bytes) & ~15ull;
+    if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+}
 
 #ifdef FRX_EXACT  // reference-order build only: the banded system in the reference's own elimination order
 // K1 ---------------------------------------------------------------------------------------------
@@ -1369,6 +1374,13 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     int* wpi = reinterpret_cast<int*>(nG + 4 * M);
     PHASE_MARK(0, 0);
 
+    // this trajectory's x and vertex ranges -> L2, one bulk prefetch each, issued before anything depends on them
+    if (tid == 32) bulk_prefetch_l2(x, sizeof(double) * (size_t)(bv.x_off[b + 1] - bv.x_off[b]));
+    if (tid == 33 && M > 1) {
+        const double* v0 = bv.verts + 3 * (size_t)bv.wp_vert_off[p0];
+        const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
+        bulk_prefetch_l2(v0, (size_t)((const char*)v1 - (const char*)v0));
+    }
     // waypoint index tables (free dimension, xi offset, vertex offset): one round trip instead of one per use
     for (int i = tid; i < M - 1; i += 64) {
         wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
@@ -1491,30 +1503,32 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             nr0 = nR[12 + d], nr1 = nR[15 + d];
         }
         for (int j = 1; j < M; j++) {
+            // Dependent chain of the recurrence, kept as short as it gets: 1/det (7 levels) runs beside N = L adj(D) L^T
+            // (4 levels), then ONE fma per entry:  D'_{j+1} = D_{j+1} - N / det.  Everything else hangs off the side.
             const double det = fma(d11, d22, -(d12 * d12));
             const double id = fast_rcp(det);
+            const double l11 = nl11, l12 = nl12, l21 = nl21, l22 = nl22;  // L_{j+1} (zeros after the last node)
+            const double c11 = nd11, c12 = nd12, c22 = nd22, r0 = nr0, r1 = nr1;
+            const double t11 = l11 * d22 - l12 * d12, t12 = l12 * d11 - l11 * d12;  // L adj(D_j)
+            const double t21 = l21 * d22 - l22 * d12, t22 = l22 * d11 - l21 * d12;
+            const double n11 = t11 * l11 + t12 * l12, n12 = t11 * l21 + t12 * l22, n22 = t21 * l21 + t22 * l22;
             const double i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;  // inverse pivot block
+            d11 = fma(-n11, id, c11), d12 = fma(-n12, id, c12), d22 = fma(-n22, id, c22);
+            if (j + 2 < M) {
+                const int q = j + 2;
+                nl11 = nL[4 * q], nl12 = nL[4 * q + 1], nl21 = nL[4 * q + 2], nl22 = nL[4 * q + 3];
+                nd11 = nD[3 * q], nd12 = nD[3 * q + 1], nd22 = nD[3 * q + 2];
+                nr0 = nR[6 * q + d], nr1 = nR[6 * q + 3 + d];
+            }
             const double w0 = i11 * z0 + i12 * z1, w1 = i12 * z0 + i22 * z1;  // w_j = Di_j z_j
             nR[6 * j + d] = w0;
             nR[6 * j + 3 + d] = w1;
-            if (d == 0) fac[NODE_F * j + 0] = i11, fac[NODE_F * j + 1] = i12, fac[NODE_F * j + 2] = i22;
-            if (j + 1 < M) {
-                const double l11 = nl11, l12 = nl12, l21 = nl21, l22 = nl22;
-                const double c11 = nd11, c12 = nd12, c22 = nd22, r0 = nr0, r1 = nr1;
-                if (j + 2 < M) {
-                    const int q = j + 2;
-                    nl11 = nL[4 * q], nl12 = nL[4 * q + 1], nl21 = nL[4 * q + 2], nl22 = nL[4 * q + 3];
-                    nd11 = nD[3 * q], nd12 = nD[3 * q + 1], nd22 = nD[3 * q + 2];
-                    nr0 = nR[6 * q + d], nr1 = nR[6 * q + 3 + d];
-                }
-                const double g11 = l11 * i11 + l12 * i12, g12 = l11 * i12 + l12 * i22;  // G_{j+1} = L_{j+1} Di_j
-                const double g21 = l21 * i11 + l22 * i12, g22 = l21 * i12 + l22 * i22;
-                d11 = c11 - (g11 * l11 + g12 * l12);  // D_{j+1} - G L^T
-                d12 = c12 - (g11 * l21 + g12 * l22);
-                d22 = c22 - (g21 * l21 + g22 * l22);
-                z0 = r0 - (l11 * w0 + l12 * w1);  // r_{j+1} - L_{j+1} w_j
-                z1 = r1 - (l21 * w0 + l22 * w1);
-                if (d == 0) {
+            z0 = r0 - (l11 * w0 + l12 * w1);  // r_{j+1} - L_{j+1} w_j
+            z1 = r1 - (l21 * w0 + l22 * w1);
+            if (d == 0) {
+                fac[NODE_F * j + 0] = i11, fac[NODE_F * j + 1] = i12, fac[NODE_F * j + 2] = i22;
+                if (j + 1 < M) {
+                    const double g11 = t11 * id, g12 = t12 * id, g21 = t21 * id, g22 = t22 * id;  // G_{j+1} = L_{j+1} Di_j
                     double* gs = nG + 4 * (j + 1);
                     gs[0] = g11, gs[1] = g12, gs[2] = g21, gs[3] = g22;
                     double* gg = fac + NODE_F * (j + 1) + 3;
@@ -1600,6 +1614,13 @@ __global__ void __launch_bounds__(64)
     const double* cg_ = bv.c + 18 * (size_t)p0;
     const double* gd_ = bv.gdC + 18 * (size_t)p0;
     const double* tailst = bv.headtail + 18 * (size_t)b + 9;  // tail p (0..2), v (3..5), a (6..8)
+    // what the epilogue streams (x, the vertex range): one bulk L2 prefetch each, long before it is needed
+    if (tid == 32) bulk_prefetch_l2(x, sizeof(double) * (size_t)nx);
+    if (tid == 33 && M > 1) {
+        const double* v0 = bv.verts + 3 * (size_t)bv.wp_vert_off[p0];
+        const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
+        bulk_prefetch_l2(v0, (size_t)((const char*)v1 - (const char*)v0));
+    }
     // K1's factors -> shared memory, asynchronously (8 doubles per node)
     {
         const double* fg = bv.lu + (size_t)NODE_F * p0;
@@ -1651,25 +1672,46 @@ __global__ void __launch_bounds__(64)
         // ---- S mu = dJ/dy with K1's factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
         if (lane < 3 && M > 1) {
             const int d = lane;
+            // both sweeps are chains of two FMAs per node; the operands of the next node are loaded into registers before
+            // this node's results are stored (the stores would otherwise fence the loads: same shared array)
             double z0 = Z[6 + d], z1 = Z[9 + d];
-            {
-                const double* f = fc + NODE_F;
-                Z[6 + d] = f[0] * z0 + f[1] * z1;
-                Z[9 + d] = f[1] * z0 + f[2] * z1;
+            double f0 = fc[NODE_F], f1 = fc[NODE_F + 1], f2 = fc[NODE_F + 2];
+            double g0 = 0, g1 = 0, g2 = 0, g3 = 0, b0 = 0, b1 = 0;
+            if (M > 2) {
+                const double* f = fc + 2 * NODE_F;
+                g0 = f[3], g1 = f[4], g2 = f[5], g3 = f[6];
+                b0 = Z[12 + d], b1 = Z[15 + d];
             }
-            for (int j = 2; j < M; j++) {
-                const double* f = fc + NODE_F * j;
-                const double t0 = Z[6 * j + d] - (f[3] * z0 + f[4] * z1);
-                const double t1 = Z[6 * j + 3 + d] - (f[5] * z0 + f[6] * z1);
+            for (int j = 1; j < M; j++) {
+                const double w0 = f0 * z0 + f1 * z1, w1 = f1 * z0 + f2 * z1;  // w_j = Di_j z_j
+                const double t0 = b0 - (g0 * z0 + g1 * z1), t1 = b1 - (g2 * z0 + g3 * z1);  // z_{j+1} = b_{j+1} - G_{j+1} z_j
+                if (j + 1 < M) {
+                    const double* f = fc + NODE_F * (j + 1);
+                    f0 = f[0], f1 = f[1], f2 = f[2];
+                }
+                if (j + 2 < M) {
+                    const double* f = fc + NODE_F * (j + 2);
+                    g0 = f[3], g1 = f[4], g2 = f[5], g3 = f[6];
+                    b0 = Z[6 * (j + 2) + d], b1 = Z[6 * (j + 2) + 3 + d];
+                }
+                Z[6 * j + d] = w0;
+                Z[6 * j + 3 + d] = w1;
                 z0 = t0, z1 = t1;
-                Z[6 * j + d] = f[0] * z0 + f[1] * z1;
-                Z[6 * j + 3 + d] = f[1] * z0 + f[2] * z1;
             }
             double m0 = Z[6 * (M - 1) + d], m1 = Z[6 * (M - 1) + 3 + d];
+            if (M > 2) {
+                const double* g = fc + NODE_F * (M - 1) + 3;
+                g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+                b0 = Z[6 * (M - 2) + d], b1 = Z[6 * (M - 2) + 3 + d];
+            }
             for (int j = M - 2; j >= 1; j--) {
-                const double* g = fc + NODE_F * (j + 1) + 3;
-                const double t0 = Z[6 * j + d] - (g[0] * m0 + g[2] * m1);
-                const double t1 = Z[6 * j + 3 + d] - (g[1] * m0 + g[3] * m1);
+                const double t0 = b0 - (g0 * m0 + g2 * m1);  // mu_j = w_j - G_{j+1}^T mu_{j+1}
+                const double t1 = b1 - (g1 * m0 + g3 * m1);
+                if (j > 1) {
+                    const double* g = fc + NODE_F * j + 3;
+                    g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+                    b0 = Z[6 * (j - 1) + d], b1 = Z[6 * (j - 1) + 3 + d];
+                }
                 m0 = t0, m1 = t1;
                 Z[6 * j + d] = m0;
                 Z[6 * j + 3 + d] = m1;
@@ -1723,13 +1765,6 @@ __global__ void __launch_bounds__(64)
         }
         const double pn = __shfl_sync(0xffffffffu, part, 1), sT = __shfl_sync(0xffffffffu, part, 2);
         if (lane == 0) cost_out[b] = (part + pn) + par.rho * sT;
-        // pull x and the vertex range of this trajectory towards L2 for addLayerPGrad
-        for (int o = lane * 16; o < nx; o += 32 * 16) prefetch_l2(x + o);
-        if (M > 1) {
-            const double* v0 = bv.verts + 3 * (size_t)bv.wp_vert_off[p0];
-            const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
-            for (const double* q = v0 + lane * 16; q < v1; q += 32 * 16) prefetch_l2(q);
-        }
     }
     __syncthreads();
     PHASE_MARK(2, 4);

@@ -143,6 +143,13 @@ int frx_batch_set_reference_order(frx_batch *b, int on);
 /* Device-time (ms, CUDA events on the batch stream) of the last eval / optimize call. */
 double frx_batch_last_ms(const frx_batch *b);
 
+/* One process (or thread) per GPU: NUMA node of the GPU (-1 = unknown), and "move the calling thread and the threads it
+ * creates later to that node's CPUs and prefer its memory" — call it first in each rank of a multi-GPU job.  The batch's
+ * pinned host buffers are placed on the GPU's node regardless (FRX_NUMA=0 disables both).  The reference is a single
+ * process on device 0 (cuda_computer::setup, cuda_computer.cu:414) and has no counterpart. */
+int frx_device_numa_node(int device_ordinal);
+int frx_bind_thread_to_device(int device_ordinal);
+
 const char *frx_strerror(int status);
 const char *frx_version(void);
 

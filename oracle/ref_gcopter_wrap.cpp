@@ -1,11 +1,13 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.
 // Compiles the reference's hot-path headers VERBATIM, from where they lie under /root/reference:
 //     se3gcopter_cpu.hpp (MINCO_S3 + SE3GCOPTER), trajectory.hpp (BandedSystem, Piece, Trajectory), lbfgs.hpp
-// over the Eigen-API shim in oracle/eigen_shim (the image has no Eigen).  Two of the reference's headers are
-// kept OUT by pre-defining their include guards, because they are off the hot path and need far more of Eigen:
-//   * root_finder.hpp — only used by Piece::getMaxVelRate/AccRate for the printed report (MinCoPlan_CPU.cpp:131-132);
+// over the Eigen-API shim in oracle/eigen_shim (the image has no Eigen).  root_finder.hpp (Piece::getMaxVelRate/AccRate,
+// the printed report of MinCoPlan_CPU.cpp:131-132) is compiled verbatim too — its one use of a dense eigen-solver
+// (eigenSolveRealRoots, root_finder.hpp:409) is never reached because the trajectory code always isolates roots.
+// ONE header is kept out by pre-defining its include guard in THIS translation unit:
 //   * geoutils.hpp (+ sdlp.hpp, quickhull.hpp) — the H->V polytope conversion of SE3GCOPTER::extractVs; the V-polytopes
-//     are SUPPLIED instead (the same ones the oracle / product use), through the geoutils::enumerateVs stub below.
+//     are SUPPLIED here (the same ones the oracle / product use), through the geoutils::enumerateVs stub below, so that
+//     evaluation parity does not depend on vertex order.  The verbatim geometry is compiled separately (ref_geoutils_wrap.cpp).
 // Built by oracle/Makefile into oracle/_ref/libfrx_ref.so; no reference source is copied into this repository.
 #include <cfloat>
 #include <cmath>
@@ -18,18 +20,7 @@
 
 #include "../include/frx.h"
 
-#define ROOT_FINDER_HPP
 #define GEOUTILS_HPP
-namespace RootFinder {  // reporting-only helpers: never called through this wrapper
-template <class A>
-inline Eigen::VectorXd polySqr(const A&) { return Eigen::VectorXd(1); }
-template <class A>
-inline double polyVal(const A&, double) { return 1.0; }
-template <class A>
-inline std::set<double> solvePolynomial(const A&, double, double, double, bool = true) { return std::set<double>(); }
-template <class A>
-inline int countRoots(const A&, double, double) { return 0; }
-}  // namespace RootFinder
 namespace geoutils {
 // V-polytopes (absolute vertex coordinates, 3 x V) handed to the reference's extractVs in call order.
 static std::deque<Eigen::MatrixXd> g_supplied;
@@ -143,6 +134,53 @@ double ref_optimize(void* hv, double rel_tol, double* durations, double* coeffs)
             for (int d = 0; d < 3; d++) coeffs[18 * i + 3 * col + d] = cm(d, col);
     }
     return j;
+}
+
+// ---- the reference's own Trajectory / Piece containers (trajectory.hpp:43-593), for the output side of the path ----
+static Trajectory make_traj(const double* durations, const double* coeffs, int pieces) {
+    Trajectory traj;
+    for (int i = 0; i < pieces; i++) {
+        CoefficientMat cm;
+        for (int col = 0; col < 6; col++)
+            for (int d = 0; d < 3; d++) cm(d, col) = coeffs[18 * i + 3 * col + d];  // 3x6 column-major, highest order first
+        traj.emplace_back(durations[i], cm);
+    }
+    return traj;
+}
+// summary[0..2] = total duration, max velocity rate, max acceleration rate (MinCoPlan_CPU.cpp:131-133);
+// per query time t: 24 doubles = pos, vel, acc, jer, rotation (row-major x|y|z columns -> xB, yB, zB), tilt rate;
+// per piece: 18 doubles of normalizePosCoeffMat (3x6 column-major) = the payload of traj2msg (se3_planner.cpp:39-53).
+void ref_traj_query(const double* durations, const double* coeffs, int pieces, const double* ts, int nt, double yaw, double g_acc,
+                    double* summary, double* per_t, double* normalized) {
+    const Trajectory traj = make_traj(durations, coeffs, pieces);
+    summary[0] = traj.getTotalDuration();
+    summary[1] = traj.getMaxVelRate();
+    summary[2] = traj.getMaxAccRate();
+    for (int k = 0; k < nt; k++) {
+        double* o = per_t + 24 * k;
+        const Eigen::Vector3d p = traj.getPos(ts[k]), v = traj.getVel(ts[k]), a = traj.getAcc(ts[k]), j = traj.getJer(ts[k]);
+        for (int d = 0; d < 3; d++) o[d] = p(d), o[3 + d] = v(d), o[6 + d] = a(d), o[9 + d] = j(d);
+        Eigen::Matrix3d R;
+        traj.getRotation(ts[k], yaw, g_acc, R);
+        for (int c = 0; c < 3; c++)
+            for (int d = 0; d < 3; d++) o[12 + 3 * c + d] = R(d, c);
+        const Eigen::Vector3d tr = traj.getTiltRate(ts[k], g_acc);
+        for (int d = 0; d < 3; d++) o[21 + d] = tr(d);
+    }
+    for (int i = 0; i < pieces; i++) {
+        const CoefficientMat n = traj[i].normalizePosCoeffMat();
+        for (int col = 0; col < 6; col++)
+            for (int d = 0; d < 3; d++) normalized[18 * i + 3 * col + d] = n(d, col);
+    }
+}
+// checkMaxVelRate / checkMaxAccRate (trajectory.hpp:543-563) and the junction states (:481-515) at junction `junc`.
+void ref_traj_checks(const double* durations, const double* coeffs, int pieces, double vel_limit, double acc_limit, int junc,
+                     int* vel_ok, int* acc_ok, double* junc_pva) {
+    const Trajectory traj = make_traj(durations, coeffs, pieces);
+    *vel_ok = traj.checkMaxVelRate(vel_limit) ? 1 : 0;
+    *acc_ok = traj.checkMaxAccRate(acc_limit) ? 1 : 0;
+    const Eigen::Vector3d p = traj.getJuncPos(junc), v = traj.getJuncVel(junc), a = traj.getJuncAcc(junc);
+    for (int d = 0; d < 3; d++) junc_pva[d] = p(d), junc_pva[3 + d] = v(d), junc_pva[6 + d] = a(d);
 }
 
 }  // extern "C"

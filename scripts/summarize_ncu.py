@@ -1,10 +1,13 @@
 """Turns an ncu report (--set full) into the tracked summaries under profiles/:
      <tag>_ncu_full_eval.csv   one column per evaluation kernel, the metrics the round notes quote
-     <tag>_dram_traffic.json   dram bytes read + written per launch (-> roofline.traffic in bench.py)
-   usage: python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01c"""
+     <tag>_dram_traffic.json   dram bytes read + written per launch
+     <tag>_ncu_eval.json       the same plus the SASS-counted fp64 thread instructions (dfma / dmul / dadd, flops = 2 dfma + dmul +
+                               dadd) and the workload shape [B, M, S, F] (-> roofline.traffic and roofline_fp64.sass in bench.py)
+   usage: python scripts/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r02 [B M S F] [free text about the capture]"""
 import csv, io, json, subprocess, sys
 
 rep, tag = sys.argv[1], sys.argv[2]
+shape = [int(v) for v in sys.argv[3:7]] if len(sys.argv) >= 7 and all(v.isdigit() for v in sys.argv[3:7]) else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -46,4 +49,16 @@ for r in cols:
     out["kernels"][short(r[ki])] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "duration_us_under_ncu": float(r[it]) * tm[units[it]],
                                     "traffic_bytes": rd + wr}
 json.dump(out, open(tag + "_dram_traffic.json", "w"), indent=1)
+ops = {}
+for op in ("dfma", "dmul", "dadd"):
+    name = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
+    ops[op] = hdr.index(name) if name in hdr else None
+if all(v is not None for v in ops.values()):
+    for r in cols:
+        k = out["kernels"][short(r[ki])]
+        for op, i in ops.items():
+            k[op] = float(r[i].replace(",", ""))
+        k["flops"] = 2.0 * k["dfma"] + k["dmul"] + k["dadd"]
+    out["shape"] = shape
+    json.dump(out, open(tag + "_ncu_eval.json", "w"), indent=1)
 print(open(tag + "_ncu_full_eval.csv").read())

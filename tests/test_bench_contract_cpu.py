@@ -11,8 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
+    # FRX_LIB points nowhere: the reference arm must not load the product library at all (its V-polytopes come from the
+    # oracle's own enumeration) — any load_library() call would raise and fail the run
+    env = dict(os.environ, FRX_LIB="/nonexistent/libfrx.so")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                        "--ref-seconds", "4", "--pieces", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--ref-seconds", "4", "--pieces", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
@@ -21,6 +24,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["higher_is_better"] is True
     assert line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 0 and line["dtype"] == "f64"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    host = line["cpu_baseline"]["host"]  # threads actually usable: affinity mask cut by the cgroup quota, not os.cpu_count()
+    assert line["cpu_baseline"]["cores"] == host["effective"] <= host["affinity"] and line["cpu_baseline"]["one_core_value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 

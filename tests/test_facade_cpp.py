@@ -41,3 +41,61 @@ def test_trajectory_containers_cpu():
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
+
+
+def test_trajectory_containers_match_the_reference_trajectory_hpp():
+    """SURVEY §8(f-3): frx::Piece / frx::Trajectory / traj2fields against the reference's OWN trajectory.hpp + root_finder.hpp
+    (compiled verbatim over the Eigen-API shim into oracle/_ref/libfrx_ref.so) on the reference's optimised trajectories of
+    the golden fixtures: positions / derivatives, getRotation, getTiltRate, total duration, junction states, the
+    duration-normalised coefficients that traj2msg ships (se3_planner.cpp:39-53), and the max-rate report of
+    MinCoPlan_CPU.cpp:131-132 (the façade isolates roots itself instead of using root_finder.hpp)."""
+    import ctypes as C
+
+    import numpy as np
+
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libfrx_ref.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref not built on this box")
+    so = os.path.join(ROOT, "tests", "cpp", "facade_traj_capi.so")
+    r = subprocess.run(["g++", "-std=c++14", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp", "facade_traj_capi.cpp"), "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    F, R = C.CDLL(so), C.CDLL(ref_so)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    from helpers import golden_names, load_golden
+
+    for name in golden_names():
+        _, z = load_golden(name)
+        dur = np.ascontiguousarray(z["ref_opt_durations"], dtype=np.float64)
+        co = np.ascontiguousarray(z["ref_opt_coeffs"], dtype=np.float64)
+        M = len(dur)
+        total = float(dur.sum())
+        ts = np.ascontiguousarray(np.r_[0.0, np.linspace(0.013, 0.987, 41) * total, total])
+        out = {}
+        for tag, lib, fn in (("ref", R, "ref_traj_query"), ("fac", F, "facade_traj_query")):
+            summary, per_t, norm, wire = np.zeros(3), np.zeros(24 * len(ts)), np.zeros(18 * M), np.zeros(19 * M)
+            args = [dp(dur), dp(co), C.c_int(M), dp(ts), C.c_int(len(ts)), C.c_double(0.4), C.c_double(9.81), dp(summary), dp(per_t), dp(norm)]
+            if tag == "fac":
+                args.append(dp(wire))
+            getattr(lib, fn)(*args)
+            out[tag] = (summary, per_t.reshape(-1, 24), norm.reshape(M, 6, 3), wire.reshape(M, 19))
+        (rs, rt, rn, _), (fs, ft, fn_, fw) = out["ref"], out["fac"]
+        assert abs(fs[0] - rs[0]) <= 1e-15 * rs[0]
+        # max rates: the reference isolates roots to FLT_EPSILON / duration (trajectory.hpp:207), the façade to machine precision
+        assert abs(fs[1] - rs[1]) <= 1e-9 * rs[1] and abs(fs[2] - rs[2]) <= 1e-9 * rs[2], (name, fs, rs)
+        scale = np.abs(rt).max(axis=0) + 1e-300
+        assert (np.abs(ft - rt).max(axis=0) <= 1e-12 * scale).all(), (name, (np.abs(ft - rt).max(axis=0) / scale).max())
+        assert np.array_equal(fn_, rn)  # normalizePosCoeffMat: same products in the same order -> bit-identical
+        # wire format = normalised coefficients, highest order first, per axis, + the duration (traj2msg)
+        for i in range(M):
+            assert np.array_equal(fw[i, 0:6], rn[i, :, 0]) and np.array_equal(fw[i, 6:12], rn[i, :, 1]) and np.array_equal(fw[i, 12:18], rn[i, :, 2])
+            assert fw[i, 18] == dur[i]
+        for lim_scale in (0.9, 1.1):
+            res = {}
+            for tag, lib, fn in (("ref", R, "ref_traj_checks"), ("fac", F, "facade_traj_checks")):
+                vo, ao, pva = C.c_int(), C.c_int(), np.zeros(9)
+                getattr(lib, fn)(dp(dur), dp(co), C.c_int(M), C.c_double(rs[1] * lim_scale), C.c_double(rs[2] * lim_scale), C.c_int(M // 2),
+                                 C.byref(vo), C.byref(ao), dp(pva))
+                res[tag] = (vo.value, ao.value, pva)
+            assert res["ref"][:2] == res["fac"][:2] == ((0, 0) if lim_scale < 1 else (1, 1))
+            assert np.array_equal(res["ref"][2], res["fac"][2])
