@@ -52,6 +52,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(y, e, y);
 }
 
+// Same accuracy in three dependent operations instead of four: one cubically convergent step y (1 + e + e^2), e = 1 - x y
+// (the hardware seed is good to ~2^-23, so e^3 is below the rounding of a double).  Used on the 2 x 2 pivot chain of K1.
+__device__ __forceinline__ double fast_rcp3(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double p = fma(e, e, e);
+    return fma(y, p, y);
+}
+
 // CTA-wide barrier usable from warp-specialised branches (both warps of the 64-thread CTA arrive at barrier 1).
 __device__ __forceinline__ void cta_bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
@@ -114,6 +124,38 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// ---- 1-D bulk copies global -> shared memory through the TMA unit, completion on an mbarrier (sm_90+/sm_100a) ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy before the first copy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+// bytes: a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes),
+                 "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+
 // One bulk (TMA-unit) prefetch of a whole byte range into L2: the 16-byte aligned interior of [p, p + bytes).
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
     const unsigned long long a = ((unsigned long long)p + 15ull) & ~15ull, e = ((unsigned long long)p + bytes) & ~15ull;
@@ -1341,6 +1383,10 @@ __global__ void __launch_bounds__(64)
 //                   + jerk_c jerk_ct - snap_ct.a_{i+1} - snap_c.muA_{i+1} + crackle_ct.v_{i+1} + crackle_c.muV_{i+1}  at t = T_i.
 // Derivation and a numpy check against a dense restatement of the reference system: scripts/proto/reduced_minco.py.
 // =================================================================================================
+// shared memory of minco_backward_kernel in doubles (layout in its header comment); the last slot is the mbarrier
+__host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
+    return (size_t)55 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
+}
 #define NODE_F 8  // doubles per node kept in bv.lu for K3: [0..2] inverse pivot block (i11, i12, i22), [3..6] G_j = L_j Di_{j-1}
 
 // K1 (fast) -----------------------------------------------------------------------------------------
@@ -1506,12 +1552,12 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             // Dependent chain of the recurrence, kept as short as it gets: 1/det (7 levels) runs beside N = L adj(D) L^T
             // (4 levels), then ONE fma per entry:  D'_{j+1} = D_{j+1} - N / det.  Everything else hangs off the side.
             const double det = fma(d11, d22, -(d12 * d12));
-            const double id = fast_rcp(det);
+            const double id = fast_rcp3(det);
             const double l11 = nl11, l12 = nl12, l21 = nl21, l22 = nl22;  // L_{j+1} (zeros after the last node)
             const double c11 = nd11, c12 = nd12, c22 = nd22, r0 = nr0, r1 = nr1;
-            const double t11 = l11 * d22 - l12 * d12, t12 = l12 * d11 - l11 * d12;  // L adj(D_j)
-            const double t21 = l21 * d22 - l22 * d12, t22 = l22 * d11 - l21 * d12;
-            const double n11 = t11 * l11 + t12 * l12, n12 = t11 * l21 + t12 * l22, n22 = t21 * l21 + t22 * l22;
+            const double t11 = fma(l11, d22, -(l12 * d12)), t12 = fma(l12, d11, -(l11 * d12));  // L adj(D_j)
+            const double t21 = fma(l21, d22, -(l22 * d12)), t22 = fma(l22, d11, -(l21 * d12));
+            const double n11 = fma(t11, l11, t12 * l12), n12 = fma(t11, l21, t12 * l22), n22 = fma(t21, l21, t22 * l22);
             const double i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;  // inverse pivot block
             d11 = fma(-n11, id, c11), d12 = fma(-n12, id, c12), d22 = fma(-n22, id, c22);
             if (j + 2 < M) {
@@ -1520,20 +1566,20 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
                 nd11 = nD[3 * q], nd12 = nD[3 * q + 1], nd22 = nD[3 * q + 2];
                 nr0 = nR[6 * q + d], nr1 = nR[6 * q + 3 + d];
             }
-            const double w0 = i11 * z0 + i12 * z1, w1 = i12 * z0 + i22 * z1;  // w_j = Di_j z_j
+            const double w0 = fma(i11, z0, i12 * z1), w1 = fma(i12, z0, i22 * z1);  // w_j = Di_j z_j
             nR[6 * j + d] = w0;
             nR[6 * j + 3 + d] = w1;
-            z0 = r0 - (l11 * w0 + l12 * w1);  // r_{j+1} - L_{j+1} w_j
-            z1 = r1 - (l21 * w0 + l22 * w1);
-            if (d == 0) {
-                fac[NODE_F * j + 0] = i11, fac[NODE_F * j + 1] = i12, fac[NODE_F * j + 2] = i22;
-                if (j + 1 < M) {
-                    const double g11 = t11 * id, g12 = t12 * id, g21 = t21 * id, g22 = t22 * id;  // G_{j+1} = L_{j+1} Di_j
-                    double* gs = nG + 4 * (j + 1);
-                    gs[0] = g11, gs[1] = g12, gs[2] = g21, gs[3] = g22;
-                    double* gg = fac + NODE_F * (j + 1) + 3;
-                    gg[0] = g11, gg[1] = g12, gg[2] = g21, gg[3] = g22;
-                }
+            z0 = fma(-l12, w1, fma(-l11, w0, r0));  // r_{j+1} - L_{j+1} w_j
+            z1 = fma(-l22, w1, fma(-l21, w0, r1));
+            // The three lanes hold bit-identical factors: all of them store (same value, same address) instead of
+            // diverging on lane 0 — a divergent tail of a dozen instructions per node costs more than the chain itself.
+            fac[NODE_F * j + 0] = i11, fac[NODE_F * j + 1] = i12, fac[NODE_F * j + 2] = i22;
+            if (j + 1 < M) {
+                const double g11 = t11 * id, g12 = t12 * id, g21 = t21 * id, g22 = t22 * id;  // G_{j+1} = L_{j+1} Di_j
+                double* gs = nG + 4 * (j + 1);
+                gs[0] = g11, gs[1] = g12, gs[2] = g21, gs[3] = g22;
+                double* gg = fac + NODE_F * (j + 1) + 3;
+                gg[0] = g11, gg[1] = g12, gg[2] = g21, gg[3] = g22;
             }
         }
         __syncwarp(0x7u);
@@ -1542,10 +1588,20 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         double y0 = nR[6 * (M - 1) + d], y1 = nR[6 * (M - 1) + 3 + d];
         Y[6 * (M - 1) + d] = y0;
         Y[6 * (M - 1) + 3 + d] = y1;
+        double g0 = 0, g1 = 0, g2 = 0, g3 = 0, w0 = 0, w1 = 0;  // operands of node j, loaded one step ahead of the chain
+        if (M > 2) {
+            const double* g = nG + 4 * (M - 1);
+            g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+            w0 = nR[6 * (M - 2) + d], w1 = nR[6 * (M - 2) + 3 + d];
+        }
         for (int j = M - 2; j >= 1; j--) {
-            const double* g = nG + 4 * (j + 1);
-            const double t0 = nR[6 * j + d] - (g[0] * y0 + g[2] * y1);
-            const double t1 = nR[6 * j + 3 + d] - (g[1] * y0 + g[3] * y1);
+            const double t0 = fma(-g2, y1, fma(-g0, y0, w0));
+            const double t1 = fma(-g3, y1, fma(-g1, y0, w1));
+            if (j > 1) {
+                const double* g = nG + 4 * j;
+                g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
+                w0 = nR[6 * (j - 1) + d], w1 = nR[6 * (j - 1) + 3 + d];
+            }
             y0 = t0, y1 = t1;
             Y[6 * j + d] = y0;
             Y[6 * j + 3 + d] = y1;
@@ -1571,15 +1627,18 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 }
 
 // K3 (fast) -----------------------------------------------------------------------------------------
-// One trajectory per CTA of two warps: Hermite adjoint per piece, the node right-hand sides, the two substitution sweeps
-// with K1's factors (lanes 0..2 of warp 0, a chain of two FMAs per node) while warp 1 sums the cost in the reference's
-// order, the closed-form dJ/dT and dJ/dq, then mergeToCoarseGradT / addLayerTGrad / addLayerPGrad (CPU.hpp:946, :816, :897).
-// smem (doubles): Ts[M] | iT[M] | sp[9M] | ep[9M] | fc[8M] | Z[6M] | kt[3M] | gTd[M] | gT[M] | gq[3M] | gTc[coarseN+1] |
-//                 em[2M] | tfac[coarseN] | ivs, ioff [coarseN ints each] | wpi[3M ints]
+// One trajectory per CTA of two warps.  dJ/dc, c and K1's factors arrive by three 1-D bulk copies (TMA unit, one mbarrier)
+// while the index tables load; then: Hermite adjoint per piece (in place over dJ/dc), the node right-hand sides, the two
+// substitution sweeps with K1's factors (lanes 0..2 of warp 0, a chain of two FMAs per node) while warp 1 sums the cost in
+// the reference's order, the closed-form dJ/dT and dJ/dq, then mergeToCoarseGradT / addLayerTGrad / addLayerPGrad
+// (CPU.hpp:946, :816, :897).
+// smem (doubles): Ts[M] | iT[M] | SE[18M] (dJ/dc in, then per piece: start part (P,V,A) 9 | end part 9) | CS[18M] (c) |
+//                 fc[8M] (after the sweeps: kt[3M] | gT[M] | gq[3M]) | Z[6M] | gTd[M] | gTc[coarseN+1] | em[2M] | tfac[coarseN] |
+//                 ivs, ioff [coarseN ints each] | wpi[3M ints] | mbarrier
 __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int b = bv.sub_traj0 + blockIdx.x;
     if (bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
@@ -1595,25 +1654,33 @@ __global__ void __launch_bounds__(64)
     const int nx = bv.x_off[b + 1] - bv.x_off[b];
     double* Ts = sm;
     double* iT = Ts + M;
-    double* sp = iT + M;
-    double* ep = sp + 9 * (size_t)M;
-    double* fc = ep + 9 * (size_t)M;
+    double* SE = iT + M;
+    double* CS = SE + 18 * (size_t)M;
+    double* fc = CS + 18 * (size_t)M;
     double* Z = fc + NODE_F * (size_t)M;
-    double* kt = Z + 6 * (size_t)M;
-    double* gTd = kt + 3 * (size_t)M;
-    double* gT = gTd + M;
+    double* gTd = Z + 6 * (size_t)M;
+    double* kt = fc;  // kt[3M] | gT[M] | gq[3M] reuse the factor block: written only after the sweeps are done with it
+    double* gT = kt + 3 * (size_t)M;
     double* gq = gT + M;
-    double* gTc = gq + 3 * (size_t)M;
+    double* gTc = gTd + M;
     double* em = gTc + coarseN + 1;
     double* tfac = em + 2 * (size_t)M;
     int* ivs = reinterpret_cast<int*>(tfac + coarseN);
     int* ioff = ivs + coarseN;
     int* wpi = ioff + coarseN;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm + backward_smem_doubles(M, coarseN) - 1);
     PHASE_MARK(2, 0);
 
-    const double* cg_ = bv.c + 18 * (size_t)p0;
-    const double* gd_ = bv.gdC + 18 * (size_t)p0;
     const double* tailst = bv.headtail + 18 * (size_t)b + 9;  // tail p (0..2), v (3..5), a (6..8)
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned bc = 144u * (unsigned)M, bf = 8u * NODE_F * (unsigned)M;
+        mbar_expect_tx(mbar, 2 * bc + bf);
+        bulk_g2s(SE, bv.gdC + 18 * (size_t)p0, bc, mbar);
+        bulk_g2s(CS, bv.c + 18 * (size_t)p0, bc, mbar);
+        bulk_g2s(fc, bv.lu + (size_t)NODE_F * p0, bf, mbar);
+    }
     // what the epilogue streams (x, the vertex range): one bulk L2 prefetch each, long before it is needed
     if (tid == 32) bulk_prefetch_l2(x, sizeof(double) * (size_t)nx);
     if (tid == 33 && M > 1) {
@@ -1621,30 +1688,38 @@ __global__ void __launch_bounds__(64)
         const double* v1 = bv.verts + 3 * ((size_t)bv.wp_vert_off[p0 + M - 2] + bv.wp_vert_cnt[p0 + M - 2]);
         bulk_prefetch_l2(v0, (size_t)((const char*)v1 - (const char*)v0));
     }
-    // K1's factors -> shared memory, asynchronously (8 doubles per node)
-    {
-        const double* fg = bv.lu + (size_t)NODE_F * p0;
-        for (int e = tid; e < NODE_F * M / 2; e += 64) cp_async16(fc + 2 * e, fg + 2 * e);
-        cp_async_commit();
-    }
-    // ---- Hermite adjoint per piece: (P0b, V0b, A0b | P1b, V1b, A1b) = H(T_i)^T dJ/dc_i, and dc/dT at fixed end states ----
     for (int i = tid; i < M; i += 64) {
         const double t = bv.T[p0 + i];
-        const double i1 = 1.0 / t, i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2, i5 = i4 * i1;
-        Ts[i] = t, iT[i] = i1;
-        const double* ci = cg_ + 18 * (size_t)i;
-        const double* gi = gd_ + 18 * (size_t)i;
+        Ts[i] = t, iT[i] = 1.0 / t;
+    }
+    for (int i = tid; i < M - 1; i += 64) {
+        wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
+        wpi[M + i] = bv.wp_xi_off[p0 + i];
+        wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+    }
+    mbar_wait(mbar, 0);
+    __syncthreads();
+    PHASE_MARK(2, 1);
+    // ---- Hermite adjoint per piece: (P0b, V0b, A0b | P1b, V1b, A1b) = H(T_i)^T dJ/dc_i, and dc/dT at fixed end states ----
+    for (int i = tid; i < M; i += 64) {
+        const double t = Ts[i];
+        const double i1 = iT[i], i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2, i5 = i4 * i1;
+        const double* ci = CS + 18 * (size_t)i;
+        double* gi = SE + 18 * (size_t)i;
+        double gv[18];
+#pragma unroll
+        for (int q = 0; q < 18; q++) gv[q] = gi[q];
         double s = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            const double g0 = gi[d], g1 = gi[3 + d], g2 = gi[6 + d], g3 = gi[9 + d], g4 = gi[12 + d], g5 = gi[15 + d];
+            const double g0 = gv[d], g1 = gv[3 + d], g2 = gv[6 + d], g3 = gv[9 + d], g4 = gv[12 + d], g5 = gv[15 + d];
             const double dP = (10.0 * i3) * g3 - (15.0 * i4) * g4 + (6.0 * i5) * g5;
             const double V0b = g1 - (6.0 * i2) * g3 + (8.0 * i3) * g4 - (3.0 * i4) * g5;
             const double V1b = (7.0 * i3) * g4 - (4.0 * i2) * g3 - (3.0 * i4) * g5;
             const double A0b = 0.5 * g2 - (1.5 * i1) * g3 + (1.5 * i2) * g4 - (0.5 * i3) * g5;
             const double A1b = (0.5 * i1) * g3 - i2 * g4 + (0.5 * i3) * g5;
-            sp[9 * i + d] = g0 - dP, sp[9 * i + 3 + d] = V0b, sp[9 * i + 6 + d] = A0b;
-            ep[9 * i + d] = dP, ep[9 * i + 3 + d] = V1b, ep[9 * i + 6 + d] = A1b;
+            gi[d] = g0 - dP, gi[3 + d] = V0b, gi[6 + d] = A0b;       // start part
+            gi[9 + d] = dP, gi[12 + d] = V1b, gi[15 + d] = A1b;      // end part
             const double V1 = (i + 1 < M) ? ci[18 + 3 + d] : tailst[3 + d];
             const double A1 = (i + 1 < M) ? 2.0 * ci[18 + 6 + d] : tailst[6 + d];
             const double J1 = 6.0 * ci[9 + d] + (24.0 * t) * ci[12 + d] + (60.0 * t * t) * ci[15 + d];
@@ -1652,22 +1727,14 @@ __global__ void __launch_bounds__(64)
         }
         gTd[i] = s;
     }
-    if (warp == 1) {
-        for (int i = lane; i < M - 1; i += 32) {
-            wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
-            wpi[M + i] = bv.wp_xi_off[p0 + i];
-            wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
-        }
-    }
     __syncthreads();
     // ---- node right-hand sides: dJ/dy_j = end part of piece j-1 + start part of piece j ----
     for (int e = tid; e < 6 * (M - 1); e += 64) {
         const int j = 1 + e / 6, r = e - 6 * (j - 1);  // r = 0..2: velocity, 3..5: acceleration
-        Z[6 * j + r] = ep[9 * (j - 1) + 3 + r] + sp[9 * j + 3 + r];
+        Z[6 * j + r] = SE[18 * (j - 1) + 12 + r] + SE[18 * j + 3 + r];
     }
-    cp_async_wait<0>();
     __syncthreads();
-    PHASE_MARK(2, 1);
+    PHASE_MARK(2, 2);
     if (warp == 0) {
         // ---- S mu = dJ/dy with K1's factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
         if (lane < 3 && M > 1) {
@@ -1684,7 +1751,7 @@ __global__ void __launch_bounds__(64)
             }
             for (int j = 1; j < M; j++) {
                 const double w0 = f0 * z0 + f1 * z1, w1 = f1 * z0 + f2 * z1;  // w_j = Di_j z_j
-                const double t0 = b0 - (g0 * z0 + g1 * z1), t1 = b1 - (g2 * z0 + g3 * z1);  // z_{j+1} = b_{j+1} - G_{j+1} z_j
+                const double t0 = fma(-g1, z1, fma(-g0, z0, b0)), t1 = fma(-g3, z1, fma(-g2, z0, b1));  // z_{j+1} = b_{j+1} - G_{j+1} z_j
                 if (j + 1 < M) {
                     const double* f = fc + NODE_F * (j + 1);
                     f0 = f[0], f1 = f[1], f2 = f[2];
@@ -1705,8 +1772,8 @@ __global__ void __launch_bounds__(64)
                 b0 = Z[6 * (M - 2) + d], b1 = Z[6 * (M - 2) + 3 + d];
             }
             for (int j = M - 2; j >= 1; j--) {
-                const double t0 = b0 - (g0 * m0 + g2 * m1);  // mu_j = w_j - G_{j+1}^T mu_{j+1}
-                const double t1 = b1 - (g1 * m0 + g3 * m1);
+                const double t0 = fma(-g2, m1, fma(-g0, m0, b0));  // mu_j = w_j - G_{j+1}^T mu_{j+1}
+                const double t1 = fma(-g3, m1, fma(-g1, m0, b1));
                 if (j > 1) {
                     const double* g = fc + NODE_F * j + 3;
                     g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3];
@@ -1771,7 +1838,7 @@ __global__ void __launch_bounds__(64)
     // ---- dJ/dT (energy + penalty partial from K2, the two closed forms above, rho of CPU.hpp:989) and crackle(ct) ----
     for (int i = tid; i < M; i += 64) {
         const double t = Ts[i], i1 = iT[i], i2 = i1 * i1, i3 = i2 * i1, i4 = i2 * i2;
-        const double* ci = cg_ + 18 * (size_t)i;
+        const double* ci = CS + 18 * (size_t)i;
         double s = 0.0;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
@@ -1798,7 +1865,7 @@ __global__ void __launch_bounds__(64)
     // ---- dJ/dq (addPropCtoP): waypoint w = node w+1 ----
     for (int e = tid; e < 3 * (M - 1); e += 64) {
         const int w = e / 3, d = e - 3 * w;
-        gq[e] = (ep[9 * w + d] + sp[9 * (w + 1) + d]) + (kt[3 * (w + 1) + d] - kt[3 * w + d]);
+        gq[e] = (SE[18 * w + 9 + d] + SE[18 * (w + 1) + d]) + (kt[3 * (w + 1) + d] - kt[3 * w + d]);
     }
     __syncthreads();
     PHASE_MARK(2, 5);
@@ -1902,9 +1969,7 @@ size_t backward_smem_bytes(int M, int coarseN) {
 size_t forward_smem_bytes(int M, int coarseN) {  // see the layout comment of minco_forward_kernel
     return sizeof(double) * ((size_t)coarseN + 1 + (size_t)28 * M + 9 + (3 * (size_t)M + 1) / 2 + 2);
 }
-size_t backward_smem_bytes(int M, int coarseN) {  // see the layout comment of minco_backward_kernel
-    return sizeof(double) * ((size_t)44 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 2);
-}
+size_t backward_smem_bytes(int M, int coarseN) { return sizeof(double) * backward_smem_doubles(M, coarseN); }
 #endif
 
 PenaltyLaunch plan_penalty(const BatchView& bv) {

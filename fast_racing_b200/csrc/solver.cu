@@ -1,14 +1,11 @@
 // Batched device-side L-BFGS — see solver.cuh for the design.
 #include "solver.cuh"
 
-#include <cooperative_groups.h>
-
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
-namespace cg = cooperative_groups;
 
 #ifdef FRX_EXACT
 #define FRX_IMPL frx_exact
@@ -592,471 +589,6 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
     }
     UPD_MARK(10);
 }
-#ifndef FRX_EXACT
-// ---------------------------------------------------------------------------------------------
-// lbfgs_update_cluster_kernel — the same update as lbfgs_update_kernel (vector-free direction), with ONE THREAD-BLOCK
-// CLUSTER PER TRAJECTORY: the CTAs of a cluster split the variable vector, partial dot products meet through distributed
-// shared memory, so a trajectory's two history passes run at the bandwidth of `C` SMs instead of one (the latency floor of a
-// sparse solver tick) and fewer trajectories are in flight at a time (what pass 1 streamed is still in L2 for pass 2).
-//
-// Determinism: the variable vector is cut into NCH = 8 FIXED chunks; every sum is formed per chunk (fixed intra-CTA order)
-// and the chunk sums are combined by a fixed pairwise tree — by the owning CTA for its own chunks, then across the cluster
-// ranks.  The tree is the same whatever the cluster size (1, 2, 4 or 8), so results do not depend on it.
-//
-// Cluster protocol ("pull"): a CTA publishes its partials in its OWN shared memory, cluster.sync(), then whoever needs them
-// reads every rank's copy through DSMEM and combines them in tree order.  All CTAs obtain bit-identical totals, so each runs
-// the scalar line-search / convergence state machine redundantly on a private copy of TrajSolve and only rank 0 writes it
-// back: no decision ever has to be broadcast.  Vector updates are chunk-local (x, g, d, xp, gp, S[end], Y[end] of a chunk
-// are only ever touched by its owner), so the only cross-CTA data are the partial sums and the 2*128+1 direction
-// coefficients computed by rank 0 from the Gram matrices.
-// ---------------------------------------------------------------------------------------------
-#define NCH 8
-#define P2_EP 5  // pass 2: elements per lane per block (32 * 5 = 160 columns)
-#define P1_EL 2  // pass 1: elements per lane per trip (x 4 slots in flight)
-
-template <int N>
-__device__ __forceinline__ double tree_sum(double* v) {  // fixed pairwise tree over N = 1, 2, 4, 8 values (in place)
-#pragma unroll
-    for (int w = N; w > 1; w >>= 1)
-#pragma unroll
-        for (int i = 0; i < w / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
-    return v[0];
-}
-__device__ __forceinline__ double tree_sum_n(double* v, int n) {
-    for (int w = n; w > 1; w >>= 1)
-        for (int i = 0; i < w / 2; i++) v[i] = v[2 * i] + v[2 * i + 1];
-    return v[0];
-}
-
-// CTA-wide sums of K values held per thread; result valid in ALL threads.  red: K * 8 doubles.
-template <int K>
-__device__ __forceinline__ void block_sum(double (&v)[K], double* red) {
-#pragma unroll
-    for (int k = 0; k < K; k++)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0)
-#pragma unroll
-        for (int k = 0; k < K; k++) red[k * 8 + (threadIdx.x >> 5)] = v[k];
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        double t = 0.0;
-#pragma unroll
-        for (int w = 0; w < UPD_THREADS / 32; w++) t += red[k * 8 + w];
-        v[k] = t;
-    }
-}
-
-__global__ void __launch_bounds__(UPD_THREADS, 2) lbfgs_update_cluster_kernel(SolverView sv) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int C = (int)cluster.num_blocks();
-    const int rank = (int)cluster.block_rank();
-    const int b = blockIdx.x / C;
-    TrajSolve* stg = sv.st + b;
-    if (stg->phase == PH_DONE) return;  // uniform over the cluster
-    extern __shared__ double dsm[];     // pass 1: pc[W][128][5] chunk partials (-> subtree sums in pc[0]); pass 2: red2[8][160]
-    __shared__ double red[5 * 8];
-    __shared__ double pA[5], pD[1];     // published partials (tree-summed over this CTA's chunks)
-    __shared__ double tot[6];
-    __shared__ double ca[128], cb[128];  // direction coefficients (rank 0 computes, the others pull)
-    __shared__ double sh_dgc;
-    __shared__ TrajSolve lst;
-    __shared__ int sh_act, sh_revert, sh_next;
-    __shared__ double sh_step;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n = sv.x_off[b + 1] - sv.x_off[b];
-    const size_t xo = (size_t)sv.x_off[b];
-    double* x = sv.x + xo;
-    double* g = sv.g + xo;
-    double* xp = sv.xp + xo;
-    double* gp = sv.gp + xo;
-    double* d = sv.d + xo;
-    const int m = sv.cfg.mem_size;
-    double* S = sv.S + (size_t)m * xo;
-    double* Y = sv.Y + (size_t)m * xo;
-    double* ysv = sv.ys + (size_t)m * b;
-    const LbfgsConfig& P = sv.cfg;
-    const double f = sv.cost[b];
-    const int W = NCH / C;               // chunks per CTA
-    const int L = (n + NCH - 1) / NCH;   // chunk length
-    const int c0 = rank * W;
-    if (tid == 0) lst = *stg;
-    __syncthreads();
-    const int phase = lst.phase;
-
-    // ---- stage A: dg = g.d, xx, gg, ys = (g-gp).(x-xp), yy = |g-gp|^2 over this CTA's chunks ----
-    {
-        double sub[5][NCH];
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            double v[5] = {0, 0, 0, 0, 0};
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) {
-                const double xi = x[i], gi = g[i], di = d[i], se = xi - xp[i], ye = gi - gp[i];
-                v[0] += gi * di, v[1] += xi * xi, v[2] += gi * gi, v[3] += ye * se, v[4] += ye * ye;
-            }
-            block_sum<5>(v, red);
-#pragma unroll
-            for (int k = 0; k < 5; k++) sub[k][cl] = v[k];
-        }
-        if (tid == 0)
-            for (int k = 0; k < 5; k++) pA[k] = tree_sum_n(sub[k], W);
-    }
-    cluster.sync();  // #1
-    if (tid < 5) {
-        double v[NCH];
-        for (int r = 0; r < C; r++) v[r] = cluster.map_shared_rank(pA, r)[tid];
-        tot[tid] = tree_sum_n(v, C);
-    }
-    __syncthreads();
-    const double dgv = tot[0], xx = tot[1], gg = tot[2], ys = tot[3], yy = tot[4];
-
-    // ---- scalar state machine (every CTA, on its private copy; identical inputs -> identical decisions) ----
-    if (tid == 0) {
-        sh_revert = 0, sh_next = 0, sh_step = 0.0;
-        if (phase == PH_INIT) {  // lbfgs.hpp:1211-1247
-            lst.n_evals = 1;
-            lst.fx = f;
-            if (P.past > 0) lst.pf[0] = f;
-            double xnorm = sqrt(xx);
-            const double gnorm = sqrt(gg);
-            if (xnorm < 1.0) xnorm = 1.0;
-            if (gnorm / xnorm <= P.g_epsilon) {
-                lst.status = LBFGS_ALREADY_MINIMIZED;
-                sh_act = ACT_FINISH;
-            } else {
-                lst.step = 1.0 / sqrt(gg);
-                lst.k = 1;
-                lst.end = 0;
-                sh_act = ACT_NEXT_ITER, sh_next = 1;  // first iteration: d = -g
-            }
-        } else {
-            lst.n_evals++;
-            int oc = (phase == PH_MT) ? lst.ls.mt_feed(f, dgv, P) : lst.ls.bt_feed(f, dgv, P);
-            lst.fx = f;
-            if (oc == LS_FAILED && phase == PH_MT) {  // lbfgs.hpp:1271-1282: restore and fall back to backtracking from xp
-                lst.step = lst.stepp;
-                lst.fx = lst.fp;
-                const double dg0 = lst.ls.dginit;
-                oc = lst.ls.bt_begin(lst.step, lst.fx, dg0, P.min_step, P.max_step, P);
-                lst.phase = PH_BT;
-            }
-            if (oc == LS_CONTINUE) {
-                sh_act = ACT_TRIAL;
-                sh_step = lst.ls.step;
-            } else if (oc == LS_FAILED) {
-                lst.status = lst.ls.code;  // lbfgs.hpp:1284-1292
-                sh_act = ACT_FINISH, sh_revert = 1;
-            } else {  // line search succeeded: lbfgs.hpp:1294-1345
-                double xnorm = sqrt(xx);
-                const double gnorm = sqrt(gg);
-                if (xnorm < 1.0) xnorm = 1.0;
-                const int k = lst.k;
-                int stop = 0;
-                if (gnorm / xnorm <= P.g_epsilon) lst.status = LBFGS_CONVERGENCE, stop = 1;
-                if (!stop && P.past > 0) {
-                    if (P.past <= k) {
-                        const double rate = (lst.pf[k % P.past] - lst.fx) / lst.fx;
-                        if (fabs(rate) < P.delta) lst.status = LBFGS_STOP, stop = 1;
-                    }
-                    if (!stop) lst.pf[k % P.past] = lst.fx;
-                }
-                if (!stop && P.max_iterations != 0 && P.max_iterations < k + 1) lst.status = LBFGSERR_MAXIMUMITERATION, stop = 1;
-                sh_act = stop ? ACT_FINISH : ACT_NEXT_ITER;
-                sh_next = stop ? 0 : 2;  // 2: a full direction update
-            }
-        }
-    }
-    __syncthreads();
-    const int next = sh_next;
-    double dg0 = 0.0;
-    bool start_iter = false;
-
-    if (sh_act == ACT_FINISH && sh_revert) {
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) x[i] = xp[i], g[i] = gp[i];
-        }
-    } else if (next == 1) {  // PH_INIT: d = -g, so g.d = -gg (same products, same order)
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) d[i] = -g[i];
-        }
-        dg0 = -gg;
-        start_iter = true;
-    } else if (next == 2) {
-        // ---- history update + vector-free direction (lbfgs.hpp:1347-1411) ----
-        const int end = lst.end, k = lst.k;
-        const int bound = (m <= k) ? m : k;
-        const int end1 = (end + 1) % m;
-        double* sn = S + (size_t)end * n;
-        double* yn = Y + (size_t)end * n;
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) sn[i] = x[i] - xp[i], yn[i] = g[i] - gp[i];
-        }
-        if (tid == 0) {
-            lst.k = k + 1;
-            lst.end = end1;
-            if (rank == 0) {
-                ysv[end] = ys;
-                if (sv.count_bytes) atomicAdd(sv.hist_bytes, 8ull * (4ull * bound + 4ull) * (unsigned long long)n);
-            }
-        }
-        __syncthreads();  // sn / yn of this CTA's chunks are read back below (by other threads of this CTA)
-        // ---- pass 1: per history slot l the five sums s_l.y_n, y_l.y_n, y_l.s_n, s_l.g, y_l.g over this CTA's chunks.
-        //      One warp per slot, four slots in flight per warp (all loads of a trip issued before use).
-        double* pc = dsm;  // [W][128][5]
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int l0 = warp; l0 < bound; l0 += 32) {  // slots l0, l0+8, l0+16, l0+24
-                double a[4][5];
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int e = 0; e < 5; e++) a[q][e] = 0.0;
-                for (int ib = i0 + lane; ib < i1; ib += 32 * P1_EL) {
-                    double yni[P1_EL], sni[P1_EL], gi[P1_EL], sv_[4][P1_EL], yv_[4][P1_EL];
-#pragma unroll
-                    for (int e = 0; e < P1_EL; e++) {
-                        const int i = ib + 32 * e;
-                        const bool in = i < i1;
-                        yni[e] = in ? yn[i] : 0.0, sni[e] = in ? sn[i] : 0.0, gi[e] = in ? g[i] : 0.0;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int l = l0 + 8 * q;
-                            const bool on = in && l < bound;
-                            sv_[q][e] = on ? S[(size_t)l * n + i] : 0.0;
-                            yv_[q][e] = on ? Y[(size_t)l * n + i] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-#pragma unroll
-                        for (int e = 0; e < P1_EL; e++) {
-                            a[q][0] += sv_[q][e] * yni[e];
-                            a[q][1] += yv_[q][e] * yni[e];
-                            a[q][2] += yv_[q][e] * sni[e];
-                            a[q][3] += sv_[q][e] * gi[e];
-                            a[q][4] += yv_[q][e] * gi[e];
-                        }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int l = l0 + 8 * q;
-#pragma unroll
-                    for (int e = 0; e < 5; e++) {
-                        const double t = warp_sum(a[q][e]);
-                        if (lane == 0 && l < bound) pc[((size_t)cl * 128 + l) * 5 + e] = t;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int t = tid; t < bound * 5; t += UPD_THREADS) {  // subtree sum over this CTA's chunks -> pc[0]
-            double v[NCH];
-            for (int cl = 0; cl < W; cl++) v[cl] = pc[(size_t)cl * 640 + t];
-            pc[t] = tree_sum_n(v, W);
-        }
-        cluster.sync();  // #2
-        if (rank == 0) {
-            // ---- Gram entries of the new pair, then the two recursions (as direction_vector_free) ----
-            __shared__ double sg[128], yg[128], tv[128], al[128];
-            __shared__ double sh_gamma;
-            double* SY = sv.SY + (size_t)b * m * m;
-            double* SYT = sv.SYT + (size_t)b * m * m;
-            double* YY = sv.YY + (size_t)b * m * m;
-            for (int t = tid; t < bound * 5; t += UPD_THREADS) {
-                double v[NCH];
-                for (int r = 0; r < C; r++) v[r] = cluster.map_shared_rank(pc, r)[t];
-                const double tv_ = tree_sum_n(v, C);
-                const int l = t / 5, e = t - 5 * l;
-                if (e == 0) SY[(size_t)l * m + end] = tv_, SYT[(size_t)end * m + l] = tv_;
-                if (e == 1) YY[(size_t)l * m + end] = tv_, YY[(size_t)end * m + l] = tv_;
-                if (e == 2 && l != end) SY[(size_t)end * m + l] = tv_, SYT[(size_t)l * m + end] = tv_;
-                if (e == 3) sg[l] = tv_;
-                if (e == 4) yg[l] = tv_;
-            }
-            __syncthreads();
-            __shared__ double tacc[128], rys[128], cbk[16];
-            __shared__ double dblk[2][16][17];
-            __shared__ int slot[128];
-            for (int l = tid; l < 128; l += UPD_THREADS) {
-                cb[l] = 0.0, ca[l] = 0.0;
-                if (l < bound) {
-                    rys[l] = 1.0 / ysv[l];
-                    slot[l] = (end - l + 2 * m) % m;  // loop 1: age o = 0 is the NEWEST pair
-                }
-            }
-            __syncthreads();
-            for (int o = tid; o < bound; o += UPD_THREADS) tacc[o] = -sg[slot[o]];
-            __syncthreads();
-            blocked_recursion<1>(SY, m, bound, tacc, rys, al, cb, dblk, cbk, slot);
-            if (tid == 0) sh_gamma = ysv[end] / YY[(size_t)end * m + end];
-            __syncthreads();
-            const double gamma = sh_gamma;
-            for (int l = tid; l < 128; l += UPD_THREADS) cb[l] *= gamma;
-            __syncthreads();
-            const double dgc = -gamma;
-            {
-                const int j = tid & 127, half = tid >> 7;
-                double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-                if (j < bound) {
-                    const int la = half * 64, lb = min(bound, la + 64);
-                    int l = la;
-                    for (; l + 4 <= lb; l += 4) {
-                        t0 += cb[l] * YY[(size_t)l * m + j];
-                        t1 += cb[l + 1] * YY[(size_t)(l + 1) * m + j];
-                        t2 += cb[l + 2] * YY[(size_t)(l + 2) * m + j];
-                        t3 += cb[l + 3] * YY[(size_t)(l + 3) * m + j];
-                    }
-                    for (; l < lb; l++) t0 += cb[l] * YY[(size_t)l * m + j];
-                }
-                if (half == 1 && j < bound) tv[j] = (t0 + t1) + (t2 + t3);
-                __syncthreads();
-                if (half == 0 && j < bound) tv[j] = dgc * yg[j] + (((t0 + t1) + (t2 + t3)) + tv[j]);
-            }
-            __syncthreads();
-            for (int o = tid; o < bound; o += UPD_THREADS) slot[o] = (end - (bound - 1) + o + 2 * m) % m;  // age 0 = OLDEST pair
-            __syncthreads();
-            for (int o = tid; o < bound; o += UPD_THREADS) tacc[o] = tv[slot[o]];
-            __syncthreads();
-            blocked_recursion<2>(SYT, m, bound, tacc, rys, al, ca, dblk, cbk, slot);
-            if (tid == 0) sh_dgc = dgc;
-        }
-        cluster.sync();  // #3
-        if (rank != 0) {
-            const double* rca = cluster.map_shared_rank(ca, 0);
-            const double* rcb = cluster.map_shared_rank(cb, 0);
-            if (tid < 128) ca[tid] = rca[tid];
-            else cb[tid - 128] = rcb[tid - 128];
-            if (tid == 0) sh_dgc = *cluster.map_shared_rank(&sh_dgc, 0);
-        }
-        __syncthreads();
-        // ---- pass 2: d = dgc*g + sum_l ca_l s_l + cb_l y_l on this CTA's chunks; lanes over columns, warps over slots ----
-        const double dgc = sh_dgc;
-        double* red2 = dsm;  // [8][32 * P2_EP]
-        double dsub[NCH];
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            double part = 0.0;
-            for (int ib = i0; ib < i1; ib += 32 * P2_EP) {
-                double acc[P2_EP];
-#pragma unroll
-                for (int e = 0; e < P2_EP; e++) acc[e] = 0.0;
-                // newest-streamed slots first: pass 1 walked the slots upwards, the tail is what the L2 holds for sure
-                for (int l = bound - 1 - warp; l >= 0; l -= 16) {
-                    const int l2 = l - 8;
-                    const double a1 = ca[l], b1 = cb[l];
-                    const double a2 = l2 >= 0 ? ca[l2] : 0.0, b2 = l2 >= 0 ? cb[l2] : 0.0;
-                    double s1[P2_EP], y1[P2_EP], s2[P2_EP], y2[P2_EP];
-#pragma unroll
-                    for (int e = 0; e < P2_EP; e++) {
-                        const int i = ib + lane + 32 * e;
-                        const bool in = i < i1;
-                        s1[e] = in ? S[(size_t)l * n + i] : 0.0;
-                        y1[e] = in ? Y[(size_t)l * n + i] : 0.0;
-                        s2[e] = (in && l2 >= 0) ? S[(size_t)l2 * n + i] : 0.0;
-                        y2[e] = (in && l2 >= 0) ? Y[(size_t)l2 * n + i] : 0.0;
-                    }
-#pragma unroll
-                    for (int e = 0; e < P2_EP; e++) acc[e] += (a1 * s1[e] + b1 * y1[e]) + (a2 * s2[e] + b2 * y2[e]);
-                }
-                __syncthreads();  // red2 free (previous block consumed)
-#pragma unroll
-                for (int e = 0; e < P2_EP; e++) red2[warp * (32 * P2_EP) + lane + 32 * e] = acc[e];
-                __syncthreads();
-                if (tid < 32 * P2_EP) {
-                    const int i = ib + tid;
-                    if (i < i1) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int w = 0; w < 8; w++) s += red2[w * (32 * P2_EP) + tid];
-                        const double gi = g[i];
-                        const double di = dgc * gi + s;
-                        d[i] = di;
-                        part += gi * di;
-                    }
-                }
-            }
-            double v[1] = {part};
-            block_sum<1>(v, red);
-            dsub[cl] = v[0];
-        }
-        if (tid == 0) pD[0] = tree_sum_n(dsub, W);
-        cluster.sync();  // #4
-        if (tid == 0) {
-            double v[NCH];
-            for (int r = 0; r < C; r++) v[r] = *cluster.map_shared_rank(pD, r);
-            tot[5] = tree_sum_n(v, C);
-            lst.step = 1.0;
-        }
-        __syncthreads();
-        dg0 = tot[5];
-        start_iter = true;
-    }
-
-    if (start_iter) {
-        // lbfgs.hpp:1248-1268: save the iterate and enter the More-Thuente search
-        if (tid == 0) {
-            lst.stepp = lst.step;
-            lst.fp = lst.fx;
-            int oc = lst.ls.mt_begin(lst.step, lst.fx, dg0, P.min_step, P.max_step, P);
-            lst.phase = PH_MT;
-            if (oc == LS_FAILED) {
-                lst.step = lst.stepp;
-                oc = lst.ls.bt_begin(lst.step, lst.fx, dg0, P.min_step, P.max_step, P);
-                lst.phase = PH_BT;
-            }
-            if (oc == LS_FAILED) {
-                lst.status = lst.ls.code;
-                sh_act = ACT_FINISH;  // x == xp already
-            } else {
-                sh_act = ACT_TRIAL;
-                sh_step = lst.ls.step;
-            }
-        }
-        __syncthreads();
-        const double stp = sh_step;
-        const bool trial = sh_act == ACT_TRIAL;
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) {
-                const double xi = x[i];
-                xp[i] = xi;
-                gp[i] = g[i];
-                if (trial) x[i] = xi + stp * d[i];  // x = xp + stp * d  (veccpy + vecadd, lbfgs.hpp:825-826)
-            }
-        }
-    } else if (sh_act == ACT_TRIAL) {
-        const double stp = sh_step;
-        for (int cl = 0; cl < W; cl++) {
-            const int i0 = (c0 + cl) * L, i1 = min(n, i0 + L);
-            for (int i = i0 + tid; i < i1; i += UPD_THREADS) {
-                double v = xp[i];
-                v += stp * d[i];
-                x[i] = v;
-            }
-        }
-    }
-    if (tid == 0 && rank == 0) {
-        if (sh_act == ACT_FINISH) {
-            lst.phase = PH_DONE;
-            sv.active[b] = 0;
-            atomicSub(sv.n_active, 1);
-        }
-        *stg = lst;
-    }
-    cluster.sync();  // nobody leaves while a peer may still read its shared memory
-}
-
-static size_t update_cluster_smem(int C) {
-    const size_t p1 = (size_t)(NCH / C) * 128 * 5, p2 = (size_t)8 * 32 * P2_EP;
-    return sizeof(double) * (p1 > p2 ? p1 : p2);
-}
-#endif  // !FRX_EXACT
-
 cudaError_t fetch_update_clocks(long long* out16, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out16, g_upd_clk, sizeof(long long) * 16);
     if (e == cudaSuccess && reset) {
@@ -1118,8 +650,6 @@ struct SolverState {
     std::vector<cudaEvent_t> ev;  // pairs around the sampled update launches
     int n_samples = 0;
     double upd_ms = 0.0, upd_bytes = 0.0;
-    int cluster = 0;      // CTAs per trajectory of the update kernel (0: the single-CTA kernel)
-    size_t smem_pad = 0;  // extra dynamic shared memory per CTA: caps the CTAs per SM, i.e. the trajectories in flight (L2 working set)
 };
 
 template <class T>
@@ -1173,26 +703,6 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
         sv.dchk = nullptr;
         if (sv.check_dir) ok = ok && dalloc(s, nx, &sv.dchk) == cudaSuccess;
     }
-#ifndef FRX_EXACT
-    {   // cluster size from the longest variable vector: a chunk (n / 8) should still give a warp a few elements per lane
-        int nmax = 0;
-        for (size_t i = 0; i + 1 < x_off.size(); i++) nmax = std::max(nmax, x_off[i + 1] - x_off[i]);
-        int c = nmax >= 768 ? 8 : (nmax >= 384 ? 4 : (nmax >= 192 ? 2 : 1));
-        if (const char* e = getenv("FRX_UPDATE_CLUSTER")) c = atoi(e);  // 0: single-CTA kernel; 1, 2, 4, 8
-        if (!(c == 0 || c == 1 || c == 2 || c == 4 || c == 8)) c = 0;
-        if (!sv.vector_free || sv.check_dir) c = 0;  // the A/B switches live in the single-CTA kernel
-        s->cluster = c;
-        int per_sm = 2;  // CTAs per SM: 148 * 2 / 8 = 37 trajectories (~96 MB of history) in flight at C = 8
-        if (const char* e = getenv("FRX_UPDATE_CTAS_PER_SM")) per_sm = std::max(1, atoi(e));
-        if (c > 0) {
-            const size_t base = update_cluster_smem(c) + 24 * 1024;  // + static shared memory, roughly
-            const size_t want = (size_t)(227 * 1024) / per_sm;
-            s->smem_pad = want > base + 1024 ? want - base - 1024 : 0;
-            const size_t dyn = update_cluster_smem(c) + s->smem_pad;
-            ok = ok && cudaFuncSetAttribute(lbfgs_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(dyn, (size_t)100 * 1024)) == cudaSuccess;
-        }
-    }
-#endif
     ok = ok && cudaMallocHost(&s->pin_int, sizeof(int) * 4) == cudaSuccess &&
          cudaMallocHost(&s->pin_dbl, sizeof(double) * 4) == cudaSuccess;
     if (!ok) {
@@ -1304,20 +814,6 @@ int solver_reset(SolverState* s, const SolverIO& io) {
 }
 
 cudaError_t solver_launch_update(SolverState* s, cudaStream_t st) {
-#ifndef FRX_EXACT
-    if (s->cluster > 0) {  // one thread-block cluster per trajectory (see lbfgs_update_cluster_kernel)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(s->sv.B * s->cluster), 1, 1);
-        cfg.blockDim = dim3(UPD_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = update_cluster_smem(s->cluster) + s->smem_pad;
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)s->cluster, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
-        cfg.attrs = at, cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, lbfgs_update_cluster_kernel, s->sv);
-    }
-#endif
     lbfgs_update_kernel<<<s->sv.B, UPD_THREADS, 0, st>>>(s->sv);
     return cudaGetLastError();
 }

@@ -4,10 +4,13 @@
 // over the Eigen-API shim in oracle/eigen_shim (the image has no Eigen).  root_finder.hpp (Piece::getMaxVelRate/AccRate,
 // the printed report of MinCoPlan_CPU.cpp:131-132) is compiled verbatim too — its one use of a dense eigen-solver
 // (eigenSolveRealRoots, root_finder.hpp:409) is never reached because the trajectory code always isolates roots.
-// ONE header is kept out by pre-defining its include guard in THIS translation unit:
-//   * geoutils.hpp (+ sdlp.hpp, quickhull.hpp) — the H->V polytope conversion of SE3GCOPTER::extractVs; the V-polytopes
-//     are SUPPLIED here (the same ones the oracle / product use), through the geoutils::enumerateVs stub below, so that
-//     evaluation parity does not depend on vertex order.  The verbatim geometry is compiled separately (ref_geoutils_wrap.cpp).
+// This file is compiled TWICE (oracle/Makefile):
+//   * libfrx_ref_full.so — everything verbatim, including geoutils.hpp + sdlp.hpp + quickhull.hpp: SE3GCOPTER::setup runs the
+//     reference's own LP + dual quickhull, so the V-polytopes (and their vertex ORDER, which defines the xi variables,
+//     SURVEY.md App. B.5) are the reference's;
+//   * libfrx_ref.so (-DREF_SUPPLIED_VPOLYS) — geoutils.hpp kept out by pre-defining its include guard; the V-polytopes are
+//     SUPPLIED (the same ones the oracle / product use) through the geoutils::enumerateVs stub below, so that evaluation
+//     parity of arbitrary workloads does not depend on vertex order.
 // Built by oracle/Makefile into oracle/_ref/libfrx_ref.so; no reference source is copied into this repository.
 #include <cfloat>
 #include <cmath>
@@ -20,6 +23,7 @@
 
 #include "../include/frx.h"
 
+#ifdef REF_SUPPLIED_VPOLYS
 #define GEOUTILS_HPP
 namespace geoutils {
 // V-polytopes (absolute vertex coordinates, 3 x V) handed to the reference's extractVs in call order.
@@ -31,6 +35,7 @@ inline bool enumerateVs(const Eigen::MatrixXd&, Eigen::MatrixXd& vPoly, const do
     return true;
 }
 }  // namespace geoutils
+#endif  // REF_SUPPLIED_VPOLYS (otherwise: the verbatim geoutils.hpp + sdlp.hpp + quickhull.hpp)
 
 #define private public
 #include "se3gcopter_cpu.hpp"  // -I /root/reference/src/plan_manage/include/se3gcopter
@@ -45,6 +50,7 @@ extern "C" {
 
 // Same problem description as the product ABI; V-polytopes are required (origin+edge form, as frx_batch_vpolys returns).
 void* ref_create(const frx_problem* p) {
+#ifdef REF_SUPPLIED_VPOLYS
     if (!p || !p->vert_off || !p->verts) return nullptr;
     geoutils::g_supplied.clear();
     const int nv = 2 * p->n_poly - 1;
@@ -56,6 +62,9 @@ void* ref_create(const frx_problem* p) {
             for (int d = 0; d < 3; d++) m(d, k) = (k == 0) ? v[d] : v[3 * k + d] + v[d];  // absolute vertex = v0 + edge
         geoutils::g_supplied.push_back(m);
     }
+#else
+    if (!p) return nullptr;  // full build: SE3GCOPTER::extractVs runs the reference's own LP + quickhull; supplied V-polytopes are ignored
+#endif
     std::vector<Eigen::MatrixXd> hPolys;
     for (int i = 0; i < p->n_poly; i++) {
         const int F = p->face_off[i + 1] - p->face_off[i];
@@ -81,6 +90,21 @@ void* ref_create(const frx_problem* p) {
     return h;
 }
 void ref_destroy(void* hv) { delete (RefHandle*)hv; }
+// The V-polytopes the reference's setup holds (cfgVs, "origin + edges" columns, se3gcopter_cpu.hpp:1049), in ITS order.
+// Two calls: verts == nullptr fills off[n_vpolys + 1]; then verts[3 * off[n_vpolys]].  Returns the number of V-polytopes.
+int ref_vpolys(void* hv, int* off, double* verts) {
+    SE3GCOPTER& o = ((RefHandle*)hv)->opt;
+    const int nv = (int)o.cfgVs.size();
+    off[0] = 0;
+    for (int i = 0; i < nv; i++) {
+        const int V = (int)o.cfgVs[i].cols();
+        if (verts)
+            for (int k = 0; k < V; k++)
+                for (int d = 0; d < 3; d++) verts[3 * (size_t)(off[i] + k) + d] = o.cfgVs[i](d, k);
+        off[i + 1] = off[i] + V;
+    }
+    return nv;
+}
 int ref_dims(void* hv, int* n, int* pieces, int* dim_t, int* dim_p) {
     RefHandle* h = (RefHandle*)hv;
     if (n) *n = h->n;

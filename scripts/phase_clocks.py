@@ -16,7 +16,7 @@ b.lib.frx_debug_phase_clocks.argtypes = [C.POINTER(C.c_longlong)]
 b.lib.frx_debug_phase_clocks(out)
 v = np.array(out[:], dtype=np.int64)
 names = {0: ["start", "forwardT/P", "node blocks", "block LDL^T + fwd subst", "back subst (+sync)", "Hermite -> c"],
-         2: ["start", "Hermite adjoint + rhs", "-", "-", "substitution sweeps / cost", "dJ/dT, dJ/dq", "merge+layerT", "layerP"]}
+         2: ["start", "bulk staging (TMA)", "Hermite adjoint + rhs", "-", "substitution sweeps / cost", "dJ/dT, dJ/dq", "merge+layerT", "layerP"]}
 for k in (0, 2):
     for w in (0, 1):
         m = v[k*32 + w*16: k*32 + w*16 + len(names[k])].astype(np.int64)
