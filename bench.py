@@ -158,6 +158,8 @@ def cpu_baseline(problems_with_v, x_list, budget_s, cores, solve_tol=None, solve
                      f"1 core: {one_core:.1f} evals/s over {reps1} evaluations",
            "one_core_value": one_core, "parallel_speedup": allc / one_core, "host": cores}
     if solve_tol is not None and solve_count > 0:
+        for o in oracles:
+            o.set_max_iterations(200000)  # safety net only (the reference has none): ~50x the iterations these solves need
         # full solves to the reference's stopping rule (lbfgs.hpp:1327-1345): one trajectory on one thread, then one per thread
         s1, r1 = ob.time_solves_mt(oracles[:1], solve_tol, 1)
         ns = min(n_or, max(nthr, 1), solve_count)
@@ -368,6 +370,7 @@ def single_solve_latency(cx, api, name, tol):
     gpu_s = time.perf_counter() - t0
     off, verts = b.vpolys(0)
     o = ob.Oracle(p.with_vpolys(off, verts))
+    o.set_max_iterations(200000)  # safety net only
     t0 = time.perf_counter()
     ro = o.optimize(tol)
     cpu_s = time.perf_counter() - t0

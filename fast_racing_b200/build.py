@@ -24,6 +24,7 @@ UNITS = [
     ("frx_capi.cu", "", []),
     ("eval_kernels.cu", "", []),
     ("solver.cu", "", []),
+    ("geometry_kernels.cu", "", ["--fmad=false"]),  # bit-identical to the host enumeration (host_geometry.cpp)
     ("host_model.cpp", "", []),
     ("host_geometry.cpp", "", []),
     ("eval_kernels.cu", "_exact", ["-DFRX_EXACT=1", "--fmad=false"]),

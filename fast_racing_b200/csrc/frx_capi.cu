@@ -16,8 +16,10 @@
 
 #include "../../include/frx.h"
 #include "device_batch.cuh"
+#include "geometry_kernels.cuh"
 #include "host_model.hpp"
 #include "solver.cuh"
+#include "waypoint_nls.hpp"
 
 #define FRX_DECLARE_EVAL_API(NS)                                                                                                   \
     namespace NS {                                                                                                                 \
@@ -195,6 +197,91 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
+// ---- batched V-polytope extraction on the device ----------------------------------------------------
+// For every problem that does not bring its own V-polytopes: all 2 n_poly - 1 polytopes (P_0, P_0^P_1, P_1, ...,
+// se3gcopter_cpu.hpp:1031-1074) of all problems go through ONE launch of enumerate_vertices_kernel; the result is handed to
+// build_model through the "supplied V-polytopes" path in the reference's "origin + edges" form (:1049).  A polytope the
+// kernel declines (GEO_FALLBACK) sends its whole problem to the host enumeration (same algorithm, same result).
+// FRX_HOST_GEOMETRY=1 forces the host path for everything.
+struct DeviceGeometry {
+    std::vector<std::vector<int>> off;       // per problem: 2 n_poly offsets (in vertices), empty = not computed here
+    std::vector<std::vector<double>> verts;  // per problem: 3 doubles per vertex column
+    std::vector<int> status;                 // per problem: FRX_OK / FRX_ERR_INFEASIBLE_GEOMETRY
+};
+static int device_geometry(const frx_problem* problems, int count, DeviceGeometry& G) {
+    G.off.assign(count, {}), G.verts.assign(count, {}), G.status.assign(count, FRX_OK);
+    const char* env = getenv("FRX_HOST_GEOMETRY");
+    if (env && env[0] == '1') return FRX_OK;
+    std::vector<double> planes;
+    std::vector<int2> polys;
+    std::vector<int> vstart, first_poly(count + 1, 0);
+    int slots = 0;
+    for (int i = 0; i < count; i++) {
+        const frx_problem& p = problems[i];
+        first_poly[i] = (int)polys.size();
+        if ((p.vert_off && p.verts) || p.n_poly < 1 || !p.face_off || !p.faces) continue;
+        bool ok = p.face_off[0] == 0;
+        for (int a = 0; a < p.n_poly && ok; a++) ok = p.face_off[a + 1] - p.face_off[a] >= 4;
+        if (!ok) continue;  // build_model reports the invalid argument
+        const int base = (int)(planes.size() / 4);
+        for (int k = 0; k < p.face_off[p.n_poly]; k++) {  // normals normalised as se3gcopter_cpu.hpp:1116, then (n, n.p)
+            const double* f = p.faces + 6 * (size_t)k;
+            const double nn = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+            const double n0 = f[0] / nn, n1 = f[1] / nn, n2 = f[2] / nn;
+            planes.push_back(n0), planes.push_back(n1), planes.push_back(n2);
+            planes.push_back(n0 * f[3] + n1 * f[4] + n2 * f[5]);
+        }
+        for (int k = 0; k < 2 * p.n_poly - 1; k++) {
+            const int a = k / 2;
+            const int F = (k % 2 == 0) ? p.face_off[a + 1] - p.face_off[a] : p.face_off[a + 2] - p.face_off[a];  // [hPs[i], hPs[i+1]] contiguous
+            polys.push_back(make_int2(base + p.face_off[a], F));
+            vstart.push_back(slots);
+            slots += 2 * F;
+        }
+    }
+    first_poly[count] = (int)polys.size();
+    const int npoly = (int)polys.size();
+    if (npoly == 0) return FRX_OK;
+    double *d_planes = nullptr, *d_verts = nullptr;
+    int2* d_polys = nullptr;
+    int *d_vstart = nullptr, *d_vcount = nullptr;
+    std::vector<double> verts(3 * (size_t)slots);
+    std::vector<int> vcount(npoly);
+    bool ok = cudaMalloc(&d_planes, sizeof(double) * planes.size()) == cudaSuccess && cudaMalloc(&d_polys, sizeof(int2) * npoly) == cudaSuccess &&
+              cudaMalloc(&d_vstart, sizeof(int) * npoly) == cudaSuccess && cudaMalloc(&d_vcount, sizeof(int) * npoly) == cudaSuccess &&
+              cudaMalloc(&d_verts, sizeof(double) * verts.size()) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_planes, planes.data(), sizeof(double) * planes.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(d_polys, polys.data(), sizeof(int2) * npoly, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(d_vstart, vstart.data(), sizeof(int) * npoly, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && frx::launch_enumerate_vertices(d_planes, d_polys, d_vstart, npoly, d_verts, d_vcount, nullptr) == cudaSuccess;
+    ok = ok && cudaMemcpy(vcount.data(), d_vcount, sizeof(int) * npoly, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(verts.data(), d_verts, sizeof(double) * verts.size(), cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(d_planes), cudaFree(d_polys), cudaFree(d_vstart), cudaFree(d_vcount), cudaFree(d_verts);
+    if (!ok) return cuda_fail(cudaGetLastError(), "device geometry");
+    for (int i = 0; i < count; i++) {
+        const int k0 = first_poly[i], k1 = first_poly[i + 1];
+        if (k1 == k0) continue;
+        bool fallback = false, infeasible = false;
+        for (int k = k0; k < k1; k++) fallback |= vcount[k] == GEO_FALLBACK, infeasible |= vcount[k] == GEO_INFEASIBLE;
+        if (fallback) continue;  // host enumeration inside build_model
+        if (infeasible) {
+            G.status[i] = FRX_ERR_INFEASIBLE_GEOMETRY;
+            continue;
+        }
+        std::vector<int>& off = G.off[i];
+        std::vector<double>& v = G.verts[i];
+        off.assign(k1 - k0 + 1, 0);
+        for (int k = k0; k < k1; k++) {
+            const double* src = &verts[3 * (size_t)vstart[k]];
+            const int V = vcount[k];
+            for (int c = 0; c < V; c++)
+                for (int d = 0; d < 3; d++) v.push_back(c == 0 ? src[d] : src[3 * c + d] - src[d]);  // origin + edges, :1049
+            off[k - k0 + 1] = off[k - k0] + V;
+        }
+    }
+    return FRX_OK;
+}
+
 extern "C" {
 
 int frx_device_numa_node(int device_ordinal) { return device_numa_node(device_ordinal); }
@@ -260,7 +347,16 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
         delete b;
         return FRX_ERR_CUDA;
     }
-    // ---- host models (geometry + tables), in parallel over problems ----
+    // ---- V-polytopes of every corridor: one launch on the device ----
+    DeviceGeometry geom;
+    {
+        const int gs = device_geometry(problems, count, geom);
+        if (gs != FRX_OK) {
+            delete b;
+            return gs;
+        }
+    }
+    // ---- host models (index tables, gridMesh; geometry only for what the device declined), in parallel over problems ----
     b->models.resize(count);
     std::vector<int> status(count, FRX_OK);
     {
@@ -268,7 +364,15 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
         std::vector<std::thread> pool;
         for (int t = 0; t < nt; t++)
             pool.emplace_back([&, t]() {
-                for (int i = t; i < count; i += nt) status[i] = build_model(problems[i], b->models[i]);
+                for (int i = t; i < count; i += nt) {
+                    if (geom.status[i] != FRX_OK) {
+                        status[i] = geom.status[i];
+                        continue;
+                    }
+                    frx_problem p = problems[i];
+                    if (!geom.off[i].empty()) p.vert_off = geom.off[i].data(), p.verts = geom.verts[i].data();
+                    status[i] = build_model(p, b->models[i]);
+                }
             });
         for (auto& th : pool) th.join();
     }
@@ -478,12 +582,60 @@ int frx_batch_initial_guess(frx_batch* b, double* x_host) {
     if (!b || !x_host) return FRX_ERR_INVALID_ARG;
     const int B = b->bv.B;
     const int nt = std::max(1, std::min<int>(std::thread::hardware_concurrency(), std::min(B, 32)));
-    std::vector<std::thread> pool;
-    for (int t = 0; t < nt; t++)
-        pool.emplace_back([&, t]() {
-            for (int i = t; i < B; i += nt) initial_guess(b->models[i], x_host + b->x_off[i]);
-        });
-    for (auto& th : pool) th.join();
+    const char* env = getenv("FRX_HOST_INIT");
+    if (env && env[0] == '1') {  // everything on the host (threaded over the batch)
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; t++)
+            pool.emplace_back([&, t]() {
+                for (int i = t; i < B; i += nt) initial_guess(b->models[i], x_host + b->x_off[i]);
+            });
+        for (auto& th : pool) th.join();
+        return FRX_OK;
+    }
+    // setInitial + backwardT on the host (sequential in the polytopes, a few hundred flops per trajectory), then the M - 1
+    // waypoint solves of backwardP per trajectory on the device, one thread each
+    CK(cudaSetDevice(b->device));
+    const int TP = b->bv.total_pieces;
+    std::vector<double> targets(3 * (size_t)TP, 0.0);
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; t++)
+            pool.emplace_back([&, t]() {
+                std::vector<double> innerP;
+                for (int i = t; i < B; i += nt) {
+                    initial_guess_prepare(b->models[i], x_host + b->x_off[i], innerP);
+                    std::copy(innerP.begin(), innerP.end(), targets.begin() + 3 * (size_t)b->piece_off[i]);
+                }
+            });
+        for (auto& th : pool) th.join();
+    }
+    std::vector<long long> work_off((size_t)TP);
+    long long total = 0;
+    for (int i = 0; i < B; i++) {
+        const TrajectoryModel& m = b->models[i];
+        for (int p = 0; p < m.fineN; p++) {
+            work_off[(size_t)b->piece_off[i] + p] = total;
+            if (p < m.fineN - 1) total += nls_work_doubles(m.vpolys[m.idxVs[p]].cols() - 1);
+        }
+    }
+    double *d_targets = nullptr, *d_work = nullptr;
+    long long* d_off = nullptr;
+    std::vector<double> xd((size_t)b->bv.total_x);
+    bool ok = cudaMalloc(&d_targets, sizeof(double) * targets.size()) == cudaSuccess && cudaMalloc(&d_off, sizeof(long long) * TP) == cudaSuccess &&
+              cudaMalloc(&d_work, sizeof(double) * (size_t)std::max<long long>(total, 1)) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_targets, targets.data(), sizeof(double) * targets.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(d_off, work_off.data(), sizeof(long long) * TP, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && frx::launch_waypoint_backward(TP, b->bv.piece_traj, b->bv.x_off, b->bv.dimT, b->bv.wp_xi_off, b->bv.wp_vert_off, b->bv.wp_vert_cnt,
+                                             b->bv.verts, d_targets, d_off, b->x_dev, d_work, b->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(xd.data(), b->x_dev, sizeof(double) * xd.size(), cudaMemcpyDeviceToHost, b->stream) == cudaSuccess &&
+         cudaStreamSynchronize(b->stream) == cudaSuccess;
+    const cudaError_t err = ok ? cudaSuccess : cudaGetLastError();
+    cudaFree(d_targets), cudaFree(d_off), cudaFree(d_work);
+    if (!ok) return cuda_fail(err, "frx_batch_initial_guess");
+    for (int i = 0; i < B; i++) {  // the xi blocks come from the device, the tau blocks were written above
+        const TrajectoryModel& m = b->models[i];
+        std::copy(xd.begin() + b->x_off[i] + m.dimT, xd.begin() + b->x_off[i + 1], x_host + b->x_off[i] + m.dimT);
+    }
     return FRX_OK;
 }
 

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "lbfgs_core.cuh"
+#include "waypoint_nls.hpp"
 
 namespace frx {
 namespace {
@@ -23,110 +24,6 @@ void vpoly_centroid(const VPolytope& vp, double* out) {
         for (int a = 0; a < k; a++) s += vp.v[3 * (a + 1) + d];
         out[d] = s / (1.0 + k) + vp.v[d];
     }
-}
-
-// ---- tiny host L-BFGS (for backwardP's per-waypoint NLS, CPU.hpp:777-813) ------------------
-// Vector work in plain sequential loops (lbfgs.hpp:422-487), scalar logic from lbfgs_core.cuh.
-template <class Eval>
-int host_lbfgs(int n, double* x, double* fx_out, Eval&& eval, const LbfgsConfig& P) {
-    auto dot = [n](const double* a, const double* b) {
-        double s = 0.;
-        for (int i = 0; i < n; i++) s += a[i] * b[i];
-        return s;
-    };
-    const int m = P.mem_size;
-    std::vector<double> g(n), xp(n), gp(n), d(n), S((size_t)m * n), Y((size_t)m * n), al(m), ysv(m), pf(std::max(P.past, 0));
-    double fx = eval(x, g.data());
-    if (!pf.empty()) pf[0] = fx;
-    for (int i = 0; i < n; i++) d[i] = -g[i];
-    double xnorm = std::sqrt(dot(x, x)), gnorm = std::sqrt(dot(g.data(), g.data()));
-    if (xnorm < 1.0) xnorm = 1.0;
-    int ret;
-    if (gnorm / xnorm <= P.g_epsilon) {
-        ret = LBFGS_ALREADY_MINIMIZED;
-    } else {
-        double step = 1.0 / std::sqrt(dot(d.data(), d.data()));
-        int k = 1, end = 0;
-        for (;;) {
-            xp.assign(x, x + n);
-            gp = g;
-            const double stepp = step, fp = fx;
-            LineSearch ls;
-            auto run = [&](bool mt) {
-                const double dg0 = dot(gp.data(), d.data());
-                int st = mt ? ls.mt_begin(step, fx, dg0, P.min_step, P.max_step, P) : ls.bt_begin(step, fx, dg0, P.min_step, P.max_step, P);
-                while (st == LS_CONTINUE) {
-                    for (int i = 0; i < n; i++) x[i] = xp[i];
-                    for (int i = 0; i < n; i++) x[i] += ls.step * d[i];
-                    fx = eval(x, g.data());
-                    const double dg = dot(g.data(), d.data());
-                    st = mt ? ls.mt_feed(fx, dg, P) : ls.bt_feed(fx, dg, P);
-                }
-                return ls.code;
-            };
-            int lsr = run(true);
-            if (lsr < 0) {
-                step = stepp, fx = fp;
-                lsr = run(false);
-            }
-            if (lsr < 0) {
-                std::copy(xp.begin(), xp.end(), x);
-                g = gp;
-                ret = lsr;
-                break;
-            }
-            step = ls.step;
-            xnorm = std::sqrt(dot(x, x)), gnorm = std::sqrt(dot(g.data(), g.data()));
-            if (xnorm < 1.0) xnorm = 1.0;
-            if (gnorm / xnorm <= P.g_epsilon) {
-                ret = LBFGS_CONVERGENCE;
-                break;
-            }
-            if (!pf.empty()) {
-                if (P.past <= k) {
-                    const double rate = (pf[k % P.past] - fx) / fx;
-                    if (std::fabs(rate) < P.delta) {
-                        ret = LBFGS_STOP;
-                        break;
-                    }
-                }
-                pf[k % P.past] = fx;
-            }
-            if (P.max_iterations != 0 && P.max_iterations < k + 1) {
-                ret = LBFGSERR_MAXIMUMITERATION;
-                break;
-            }
-            double *se = &S[(size_t)end * n], *ye = &Y[(size_t)end * n];
-            for (int i = 0; i < n; i++) se[i] = x[i] - xp[i];
-            for (int i = 0; i < n; i++) ye[i] = g[i] - gp[i];
-            const double ys = dot(ye, se), yy = dot(ye, ye);
-            ysv[end] = ys;
-            const int bound = (m <= k) ? m : k;
-            ++k;
-            end = (end + 1) % m;
-            for (int i = 0; i < n; i++) d[i] = -g[i];
-            int j = end;
-            for (int i = 0; i < bound; i++) {
-                j = (j + m - 1) % m;
-                al[j] = dot(&S[(size_t)j * n], d.data()) / ysv[j];
-                const double c = -al[j];
-                const double* yj = &Y[(size_t)j * n];
-                for (int q = 0; q < n; q++) d[q] += c * yj[q];
-            }
-            const double sc = ys / yy;
-            for (int q = 0; q < n; q++) d[q] *= sc;
-            for (int i = 0; i < bound; i++) {
-                const double beta = dot(&Y[(size_t)j * n], d.data()) / ysv[j];
-                const double c = al[j] - beta;
-                const double* sj = &S[(size_t)j * n];
-                for (int q = 0; q < n; q++) d[q] += c * sj[q];
-                j = (j + 1) % m;
-            }
-            step = 1.0;
-        }
-    }
-    if (fx_out) *fx_out = fx;
-    return ret;
 }
 
 }  // namespace
@@ -236,9 +133,10 @@ int build_model(const frx_problem& p, TrajectoryModel& m) {
     return FRX_OK;
 }
 
-void initial_guess(const TrajectoryModel& m, double* x) {
+void initial_guess_prepare(const TrajectoryModel& m, double* x, std::vector<double>& innerP) {
     // setInitial, CPU.hpp:1188-1228
-    std::vector<double> coarseT(m.coarseN), innerP(3 * (size_t)std::max(m.fineN - 1, 0));
+    std::vector<double> coarseT(m.coarseN);
+    innerP.assign(3 * (size_t)std::max(m.fineN - 1, 0), 0.0);
     const double spd = std::min(m.par.v_max, 10.0);
     {
         double lastP[3], curP[3] = {m.ini_clamped_p[0], m.ini_clamped_p[1], m.ini_clamped_p[2]}, delta[3];
@@ -277,42 +175,19 @@ void initial_guess(const TrajectoryModel& m, double* x) {
             x[i] = m.c2 ? (r > 1.0 ? (std::sqrt(2.0 * r - 1.0) - 1.0) : (1.0 - std::sqrt(2.0 / r - 1.0))) : std::log(r);
         }
     }
-    // backwardP, CPU.hpp:777-813: per waypoint, min || V r(xi)^2 + v0 - q ||^2 by L-BFGS
-    LbfgsConfig nls;
-    nls.g_epsilon = FLT_EPSILON;
-    nls.max_iterations = 128;
+}
+
+void initial_guess(const TrajectoryModel& m, double* x) {
+    std::vector<double> innerP;
+    initial_guess_prepare(m, x, innerP);
+    // backwardP, CPU.hpp:777-813: per waypoint, min || V r(xi)^2 + v0 - q ||^2 by L-BFGS (waypoint_nls.hpp)
     double* P = x + m.dimT;
+    std::vector<double> work;
     for (int i = 0; i < m.fineN - 1; i++) {
         const VPolytope& vp = m.vpolys[m.idxVs[i]];
         const int k = vp.cols() - 1;
-        double* xi = P + m.xi_off[i];
-        for (int a = 0; a < k; a++) xi[a] = 1.0 / (std::sqrt(k + 1.0) + 1.0);
-        const double* target = &innerP[3 * (size_t)i];
-        std::vector<double> r(k), gdr(k);
-        auto objective = [&](const double* pp, double* grad) {  // CPU.hpp:749-774
-            double qn = 0.0;
-            for (int a = 0; a < k; a++) qn += pp[a] * pp[a];
-            const double q1 = qn + 1.0, q1s = q1 * q1;
-            for (int a = 0; a < k; a++) r[a] = 2.0 / q1 * pp[a];
-            double delta[3];
-            for (int d = 0; d < 3; d++) {
-                double acc = 0.0;
-                for (int a = 0; a < k; a++) acc += vp.v[3 * (a + 1) + d] * (r[a] * r[a]);
-                delta[d] = acc + vp.v[d] - target[d];
-            }
-            const double cost = delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2];
-            const double g3[3] = {2 * delta[0], 2 * delta[1], 2 * delta[2]};
-            double gp = 0.0;
-            for (int a = 0; a < k; a++) {
-                const double* e = &vp.v[3 * (a + 1)];
-                gdr[a] = (e[0] * g3[0] + e[1] * g3[1] + e[2] * g3[2]) * r[a] * 2.0;
-            }
-            for (int a = 0; a < k; a++) gp += gdr[a] * pp[a];
-            for (int a = 0; a < k; a++) grad[a] = gdr[a] * 2.0 / q1 - pp[a] * 4.0 * gp / q1s;
-            return cost;
-        };
-        double minSqrD;
-        host_lbfgs(k, xi, &minSqrD, objective, nls);
+        work.resize((size_t)nls_work_doubles(k));
+        waypoint_backward(vp.v.data(), k, &innerP[3 * (size_t)i], P + m.xi_off[i], work.data());
     }
 }
 

@@ -37,11 +37,19 @@ int build_model(const frx_problem& p, TrajectoryModel& out);
 
 // setInitial + backwardT + backwardP (CPU.hpp:1237-1240): writes the n() entries of x.
 void initial_guess(const TrajectoryModel& m, double* x);
+// The sequential part alone (setInitial + backwardT): writes the tau block of x and the target waypoints innerP (3 per inner
+// waypoint); the per-waypoint solves of backwardP then run on the device (geometry_kernels.cu: waypoint_backward_kernel).
+void initial_guess_prepare(const TrajectoryModel& m, double* x, std::vector<double>& innerP);
 
-// --- geometry (replaces geoutils::findInterior / enumerateVs, geoutils.hpp:43-149) ---------
-// faces: 6*F with unit normals.  Returns false if the polytope has no interior / is unbounded.
-bool find_interior(const double* faces, int F, double interior[3]);
-// Vertex enumeration; out = 3*V vertex coordinates (absolute).  Returns false on failure.
-bool enumerate_vertices(const double* faces, int F, std::vector<double>& out, double epsilon = 1.0e-6);
+// --- geometry (replaces geoutils::findInterior / enumerateVs, geoutils.hpp:43-149; algorithm in geometry_core.hpp) ---------
+// faces: 6*F with unit normals.  out = 3*V vertex coordinates (absolute).  Returns false if the polytope has no interior, is
+// unbounded, or has more than geo::MAX_FACES faces.
+bool enumerate_vertices(const double* faces, int F, std::vector<double>& out);
+struct GeoCandidate {
+    double x[3];
+    int key;  // geo::triple_key of the face triple that produced it
+};
+void pack_planes(const double* faces, int F, double* nd);  // (n, p) rows -> (n, d = n.p) rows
+bool finish_vertices(const double* nd, int F, std::vector<GeoCandidate>& cand, std::vector<double>& out);
 
 }  // namespace frx

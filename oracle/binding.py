@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 REF_LBFGS = os.path.join(HERE, "_ref", "libref_lbfgs.so")
 REF_GCOPTER = os.path.join(HERE, "_ref", "libfrx_ref.so")
+REF_GCOPTER_FULL = os.path.join(HERE, "_ref", "libfrx_ref_full.so")  # + verbatim geoutils.hpp / sdlp.hpp / quickhull.hpp
+REF_GEO = os.path.join(HERE, "_ref", "libref_geo.so")
 
 EVAL_T = C.CFUNCTYPE(C.c_double, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
 
@@ -61,6 +63,7 @@ def lib():
         L.fro_time_solves_mt.argtypes = [P(vp), ci, cd, ci, P(cd), P(ci), P(ci), P(ci)]
         L.fro_brute_force_vertices.argtypes = [P(cd), ci, P(cd), ci]
         L.fro_vpolys.argtypes = [vp, P(ci), P(cd)]
+        L.fro_set_max_iterations.argtypes = [vp, ci]
         L.fro_banded_solve.argtypes = [P(cd), ci, P(cd), ci]
         L.fro_lbfgs_testfn.argtypes = [ci, ci, P(cd), P(cd), ci, ci, cd, cd, ci, P(ci), P(ci)]
         L.fro_testfn_eval.restype = cd
@@ -138,6 +141,10 @@ class Oracle:
         return dict(jerk_cost=j, durations=dur, coeffs=co, x=xf, final_cost=fc.value, status=st.value,
                     iterations=it.value, evaluations=ev.value)
 
+    def set_max_iterations(self, n):
+        """Safety net of timing runs (0 = no limit, as the reference): a NaN objective otherwise never stops."""
+        self.L.fro_set_max_iterations(self.h, int(n))
+
     def time_evals(self, x, reps):
         x = np.ascontiguousarray(x, dtype=np.float64)
         return self.L.fro_time_evals(self.h, _dp(x), reps)
@@ -200,15 +207,17 @@ class RefGcopter:
     built (a box that has /root/reference) or travelled with the snapshot."""
 
     _lib = None
+    PATH = REF_GCOPTER
+    NEEDS_VPOLYS = True
 
     @classmethod
     def available(cls):
-        return os.path.exists(REF_GCOPTER)
+        return os.path.exists(cls.PATH)
 
     @classmethod
     def lib(cls):
         if cls._lib is None:
-            R = C.CDLL(REF_GCOPTER)
+            R = C.CDLL(cls.PATH)
             P, vp, ci, cd = C.POINTER, C.c_void_p, C.c_int, C.c_double
             R.ref_create.restype = vp
             R.ref_create.argtypes = [vp]
@@ -221,12 +230,13 @@ class RefGcopter:
             R.ref_forward.argtypes = [vp, P(cd), P(cd), P(cd)]
             R.ref_optimize.restype = cd
             R.ref_optimize.argtypes = [vp, cd, P(cd), P(cd)]
+            R.ref_vpolys.argtypes = [vp, P(ci), P(cd)]
             cls._lib = R
         return cls._lib
 
     def __init__(self, problem):
         self.R = self.lib()
-        assert problem.vert_off is not None
+        assert problem.vert_off is not None or not self.NEEDS_VPOLYS
         self.problem = problem
         self._s = problem.as_struct()
         self.h = self.R.ref_create(C.cast(C.pointer(self._s), C.c_void_p))
@@ -278,3 +288,33 @@ class RefGcopter:
         co = np.zeros(18 * self.pieces)
         j = self.R.ref_optimize(self.h, rel_tol, _dp(dur), _dp(co))
         return dict(jerk_cost=j, durations=dur, coeffs=co)
+
+    def vpolys(self):
+        """The V-polytopes the reference's setup holds (cfgVs), origin + edge columns, in the reference's order."""
+        off = np.zeros(2 * self.problem.n_poly, np.int32)
+        self.R.ref_vpolys(self.h, _ip(off), None)
+        verts = np.zeros(3 * int(off[-1]))
+        self.R.ref_vpolys(self.h, _ip(off), _dp(verts))
+        return off, verts
+
+
+class RefGcopterFull(RefGcopter):
+    """The reference's SE3GCOPTER with NOTHING supplied: verbatim geoutils.hpp + sdlp.hpp + quickhull.hpp too, so setup() runs
+    the reference's own interior-point LP and dual quickhull (oracle/_ref/libfrx_ref_full.so).  One fresh process per use is
+    advisable when bit-reproducibility matters: sdlp keeps a function-static RNG (sdlp.hpp:693)."""
+
+    _lib = None
+    PATH = REF_GCOPTER_FULL
+    NEEDS_VPOLYS = False
+
+
+def ref_enumerate_vertices(faces):
+    """Vertices (V x 3, absolute, the reference's order) of one H-polytope by the verbatim geoutils::enumerateVs; None if empty."""
+    if not os.path.exists(REF_GEO):
+        return None
+    G = C.CDLL(REF_GEO)
+    f = np.ascontiguousarray(faces, dtype=np.float64).reshape(-1)
+    out = np.zeros(3 * 1024)
+    G.ref_enumerate_vertices.argtypes = [C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int]
+    v = G.ref_enumerate_vertices(_dp(f), len(f) // 6, _dp(out), 1024)
+    return None if v < 0 else out[: 3 * v].reshape(v, 3).copy()

@@ -902,6 +902,7 @@ struct Se3Gcopter {
 
     // CPU.hpp:1230-1268.  durations[fineN]; coeffs[fineN*18]: per piece a 3x6 column-major
     // matrix, highest order first (CPU.hpp:561, traj.hpp:39).  Returns the jerk cost only.
+    int safety_max_iterations = 0;
     double optimize(double relCostTol, double* durations, double* coeffs, double* x_final = nullptr,
                     double* penalised_cost = nullptr) {
         std::vector<double> x(dim());
@@ -912,6 +913,10 @@ struct Se3Gcopter {
         lp.g_epsilon = 1.0e-16;
         lp.min_step = 1.0e-32;
         lp.delta = relCostTol;
+        // The reference sets no iteration limit (max_iterations = 0, lbfgs.hpp:128-140): a run whose objective turns NaN never
+        // satisfies any stopping test and loops forever.  safety_max_iterations (0 = as the reference) lets the TIMING harness of
+        // bench.py bound such a run; parity tests leave it at 0.
+        lp.max_iterations = safety_max_iterations;
         double minObjectivePenalty = 0.0;
         int evals = 0;
         last_status = lbfgs_minimize(dim(), x.data(), &minObjectivePenalty, &Se3Gcopter::objectiveFunc, this, lp,

@@ -107,6 +107,9 @@ double fro_optimize(void* hv, double rel_tol, double* durations, double* coeffs,
     return j;
 }
 
+// Safety net for timing runs only (see Se3Gcopter::safety_max_iterations): 0 restores the reference's "no limit".
+void fro_set_max_iterations(void* hv, int max_iterations) { ((OracleHandle*)hv)->opt.safety_max_iterations = max_iterations; }
+
 // L-BFGS with the reference's optimize() parameters (CPU.hpp:1243-1247) from an arbitrary start x (in/out).
 double fro_optimize_from(void* hv, double* x, double rel_tol) {
     auto& o = ((OracleHandle*)hv)->opt;

@@ -28,15 +28,36 @@ CASES = {
     "sfc_small": (lambda: synth.make_problem(102, 6, 12, 8), 0.05),
     "ragged_faces": (lambda: synth.make_problem(103, 5, np.array([8, 14, 6, 20, 9]), 10, gates=(2,)), 0.1),
     "moderncity_small": (lambda: synth.make_problem(104, 7, 12, 16, params=api.MODERNCITY), 0.05),
+    # "*_refgeo": the V-polytopes are the REFERENCE'S OWN (verbatim geoutils.hpp + sdlp.hpp + quickhull.hpp through
+    # SE3GCOPTER::setup, oracle/_ref/libfrx_ref_full.so), i.e. the vertex order that defines the xi variables is the
+    # reference's; every ref_* output below then comes from the fully verbatim reference.
+    "sfc_small_refgeo": (lambda: synth.make_problem(102, 6, 12, 8), 0.05),
+    "ragged_faces_refgeo": (lambda: synth.make_problem(103, 5, np.array([8, 14, 6, 20, 9]), 10, gates=(2,)), 0.1),
 }
 
 
 def main():
     R = ob.ref_lbfgs()
     L = ob.lib()
+    only = set(sys.argv[1:])
     for name, (factory, sigma) in CASES.items():
+        if only and name not in only:
+            continue
         p = factory()
-        off, verts = api.host_vpolys(p)
+        refgeo = name.endswith("_refgeo")
+        if refgeo:
+            full = ob.RefGcopterFull(p)  # the reference's own setup(): LP interior point + dual quickhull + first-seen dedup
+            off, verts = full.vpolys()
+            po, pvv = api.host_vpolys(p)  # the product's enumeration: same vertex SETS, its own order
+            assert np.array_equal(np.diff(off), np.diff(po))
+            for k in range(len(off) - 1):
+                a = verts[3 * off[k]:3 * off[k + 1]].reshape(-1, 3).copy()
+                b = pvv[3 * po[k]:3 * po[k + 1]].reshape(-1, 3).copy()
+                a[1:] += a[0]
+                b[1:] += b[0]
+                assert np.abs(a[:, None] - b[None]).sum(-1).min(1).max() < 1e-9, (name, k)
+        else:
+            off, verts = api.host_vpolys(p)
         pv = p.with_vpolys(off, verts)
         o = ob.Oracle(pv)
         x0 = o.initial_guess()
@@ -62,7 +83,7 @@ def main():
                    opt_coeffs=r["coeffs"], opt_rel_tol=tol)
         if ob.RefGcopter.available():
             # the reference's OWN code (verbatim se3gcopter_cpu.hpp over the Eigen-API shim) on the same inputs
-            rg = ob.RefGcopter(pv)
+            rg = full if refgeo else ob.RefGcopter(pv)
             rc, rgr = zip(*[rg.eval(x) for x in xs])
             assert np.array_equal(np.array(rc), np.array(costs)) and np.array_equal(np.stack(rgr), np.stack(grads)), \
                 f"{name}: oracle deviates from the verbatim reference source"

@@ -30,6 +30,28 @@ def test_facade_runs_the_reference_call_sequence():
     assert "Final cost" in r.stdout and "infeasible corridor rejected: 1" in r.stdout
 
 
+def _build_eigen_overloads():
+    lib = os.path.join(ROOT, "fast_racing_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "facade_eigen_overloads")
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle", "eigen_shim"),
+           os.path.join(ROOT, "tests", "cpp", "facade_eigen_overloads.cpp"), "-L", lib, "-lfrx", f"-Wl,-rpath,{lib}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_facade_eigen_overloads_compile():
+    """The reference's exact call (Eigen::MatrixXd hPolys, Matrix3d states, Vector4d weights, MinCoPlan_CPU.cpp:114-124)
+    compiles against the façade's Eigen overloads; oracle/eigen_shim stands in for Eigen (not in this image)."""
+    assert os.path.exists(_build_eigen_overloads())
+
+
+@pytest.mark.gpu
+def test_facade_eigen_overloads_run():
+    r = subprocess.run([_build_eigen_overloads()], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_trajectory_containers_cpu():
     """Piece / Trajectory helpers the planner calls downstream: exact max velocity / acceleration rates
     (root isolation instead of root_finder.hpp) against 2e5-point sampling, checkMax*Rate, getRotation, normalised

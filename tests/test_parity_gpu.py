@@ -144,6 +144,50 @@ def test_batches_of_different_shapes_coexist(oracle_mod):
     bb.close()
 
 
+def test_device_vpolytope_extraction_matches_host_path(oracle_mod):
+    """SURVEY §8(f-1): frx_batch_create extracts the V-polytopes of all corridors in one kernel launch (one warp per polytope);
+    the result is bit-identical — vertices AND order — to the host enumeration (same algorithm, geometry_core.hpp), equals the
+    oracle's brute-force vertex sets, and infeasible corridors are still rejected (SE3GCOPTER::setup returning false)."""
+    probs = [synth.make_problem(81, 9, np.array([6, 8, 30, 12, 7, 9, 50, 6, 11]), 6), synth.make_problem(82, 1, 8, 4),
+             synth.config_problems("C2", 1)[0], synth.make_problem(83, 12, 12, 8)]
+    b = api.Batch(probs)
+    for i, p in enumerate(probs):
+        off_d, v_d = b.vpolys(i)
+        off_h, v_h = api.host_vpolys(p)
+        assert np.array_equal(off_d, off_h) and np.array_equal(v_d, v_h), i
+        faces = p.faces.reshape(-1, 6).copy()
+        faces[:, :3] /= np.linalg.norm(faces[:, :3], axis=1, keepdims=True)
+        for k in range(len(off_d) - 1):
+            a = v_d[3 * off_d[k]:3 * off_d[k + 1]].reshape(-1, 3).copy()
+            a[1:] += a[0]
+            j = k // 2
+            f = faces[p.face_off[j]:p.face_off[j + 1]] if k % 2 == 0 else faces[p.face_off[j]:p.face_off[j + 2]]
+            bf = oracle_mod.brute_force_vertices(f)
+            assert len(bf) == len(a) and np.abs(a[:, None] - bf[None]).sum(-1).min(1).max() < 1e-8, (i, k)
+    b.close()
+    bad = synth.make_problem(84, 3, 8, 8)
+    faces = bad.faces.reshape(-1, 6).copy()
+    faces[bad.face_off[1]:bad.face_off[2], 3:] += 1000.0  # intersection 0^1 is empty
+    with pytest.raises(api.FrxError) as e:
+        api.Batch([synth.make_problem(85, 3, 8, 8), api.Problem(bad.ini, bad.fin, bad.face_off, faces, bad.params)])
+    assert e.value.status == api.FRX_ERR_INFEASIBLE_GEOMETRY
+
+
+def test_device_initial_guess_is_bit_identical_to_host_path(monkeypatch):
+    """the M - 1 per-waypoint solves of backwardP (se3gcopter_cpu.hpp:777-813) run on the device, one thread
+    each, with the same code as the host path (waypoint_nls.hpp, no FMA contraction): identical bits — and, through the golden
+    fixtures (test_cuda_matches_golden_vectors), identical to the reference's own setInitial + backwardT + backwardP."""
+    probs = [synth.make_problem(86, 9, np.array([6, 8, 30, 12, 7, 9, 50, 6, 11]), 6), synth.make_problem(87, 1, 8, 4),
+             synth.config_problems("C2", 1)[0], synth.make_problem(88, 40, 10, 9, params=api.MODERNCITY)]
+    probs.append(api.Problem(probs[0].ini, probs[0].fin, probs[0].face_off, probs[0].faces, dict(probs[0].params, grid_res=1.1, c2_diffeo=0)))
+    b = api.Batch(probs)
+    x_dev = b.initial_guess()
+    monkeypatch.setenv("FRX_HOST_INIT", "1")
+    x_host = b.initial_guess()
+    assert np.isfinite(x_dev).all() and np.array_equal(x_dev, x_host)
+    b.close()
+
+
 def test_eval_parity_time_maps(oracle_mod):
     """Fixed total time (rho = 0) with the C2 and the exp diffeomorphism; soft time with exp."""
     p = synth.make_problem(41, 6, 10, 8)
