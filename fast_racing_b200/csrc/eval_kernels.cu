@@ -483,7 +483,10 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 #define PEN_THREADS 64
 #define CF 60  // per piece: 18 pos + 15 vel + 12 acc + 9 jerk + 6 snap coefficients
 
-__global__ void __launch_bounds__(PEN_THREADS, 8) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
+#ifndef FRX_PEN_MINBLOCKS
+#define FRX_PEN_MINBLOCKS 8  // CTAs per SM the register allocation aims at (8 x 64 threads x 128 registers = the whole file)
+#endif
+__global__ void __launch_bounds__(PEN_THREADS, FRX_PEN_MINBLOCKS) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
     const int gp_base = bv.sub_piece0 + blockIdx.x * pl.ppc;

@@ -1,6 +1,8 @@
 // Implementation of the C ABI declared in include/frx.h.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is opened at run time (dlopen), libfrx.so does not link it
 #include <sched.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -742,6 +744,46 @@ double frx_measure_fp64_tflops(void) { return frx_fast::measure_fp64_tflops(); }
 
 // Reference-order mode: evaluation and solver in the reference's operation order (no FMA contraction, sequential
 // reductions, divisions as written): bit-identical to the CPU code, slow by construction (validation / reproducibility).
+// Cross-rank arg-min for a C/C++ caller that runs one rank per GPU: the only collective of the path — one
+// ncclAllGather of {cost, global index} (16 B per rank) on the batch's stream, then a local arg-min (ties -> lowest index).
+// The NCCL library of the process is used (dlopen of libnccl.so.2; nothing is linked), `nccl_comm` is the caller's ncclComm_t.
+int frx_batch_argmin_allgather(frx_batch* b, void* nccl_comm, int n_ranks, long long global_index_offset, long long* best_global_index,
+                               double* best_cost) {
+    if (!b || !nccl_comm || n_ranks < 1 || !b->have_final) return FRX_ERR_INVALID_ARG;
+    typedef ncclResult_t (*allgather_t)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    static allgather_t allgather = nullptr;
+    if (!allgather) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        allgather = h ? (allgather_t)dlsym(h, "ncclAllGather") : nullptr;
+        if (!allgather) {
+            std::fprintf(stderr, "[frx] frx_batch_argmin_allgather: no NCCL library in this process (%s)\n", dlerror());
+            return FRX_ERR_CUDA;
+        }
+    }
+    CK(cudaSetDevice(b->device));
+    int idx = -1;
+    double val = 0.0;
+    int s = frx_batch_argmin(b, &idx, &val);
+    if (s != FRX_OK) return s;
+    double* buf = nullptr;  // [2] mine | [2 * n_ranks] everybody's
+    CK(cudaMalloc(&buf, sizeof(double) * 2 * (size_t)(n_ranks + 1)));
+    const double mine[2] = {val, (double)(global_index_offset + idx)};  // indices below 2^53 are exact in a double
+    std::vector<double> all(2 * (size_t)n_ranks);
+    bool ok = cudaMemcpyAsync(buf, mine, sizeof(mine), cudaMemcpyHostToDevice, b->stream) == cudaSuccess;
+    ok = ok && allgather(buf, buf + 2, 2, ncclDouble, (ncclComm_t)nccl_comm, b->stream) == ncclSuccess;
+    ok = ok && cudaMemcpyAsync(all.data(), buf + 2, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, b->stream) == cudaSuccess &&
+         cudaStreamSynchronize(b->stream) == cudaSuccess;
+    cudaFree(buf);
+    if (!ok) return cuda_fail(cudaGetLastError(), "frx_batch_argmin_allgather");
+    int best = 0;
+    for (int r = 1; r < n_ranks; r++)
+        if (all[2 * r] < all[2 * best] || (all[2 * r] == all[2 * best] && all[2 * r + 1] < all[2 * best + 1])) best = r;
+    if (best_cost) *best_cost = all[2 * best];
+    if (best_global_index) *best_global_index = (long long)all[2 * best + 1];
+    return FRX_OK;
+}
+
 int frx_batch_set_reference_order(frx_batch* b, int on) {
     if (!b) return FRX_ERR_INVALID_ARG;
     b->exact = on != 0;

@@ -134,6 +134,13 @@ int frx_batch_optimize(frx_batch *b, double rel_tol, double *durations, double *
  * Device-side reduction; the cross-GPU gather is the caller's (NCCL all-gather of 16 B/rank). */
 int frx_batch_argmin(frx_batch *b, int *best_traj, double *best_cost);
 
+/* Multi-GPU, one rank per GPU (the batch is sharded by the caller): arg-min over ALL ranks after
+ * frx_batch_optimize.  `nccl_comm` = the caller's ncclComm_t for these n_ranks; global_index_offset = index of this rank's
+ * first trajectory in the global batch.  One ncclAllGather of 16 B per rank on the batch stream; every rank gets the same
+ * answer (ties -> lowest global index).  NCCL is taken from the process (dlopen), libfrx.so does not link it. */
+int frx_batch_argmin_allgather(frx_batch *b, void *nccl_comm, int n_ranks, long long global_index_offset,
+                               long long *best_global_index, double *best_cost);
+
 /* Reference-order mode (on != 0): evaluation and solver run in the reference's exact operation order — no FMA
  * contraction, divisions as written, sequential reductions (the kernels are compiled a second time with --fmad=false,
  * the penalty integral and the L-BFGS dot products run sequentially).  Results are bit-identical to the reference CPU

@@ -52,6 +52,22 @@ def test_facade_eigen_overloads_run():
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.mark.gpu
+def test_c_abi_cross_rank_argmin_nccl():
+    """frx_batch_argmin_allgather from plain C++ (tests/cpp/argmin_nccl.cpp): one thread per visible GPU, ncclCommInitAll,
+    every rank must agree on the (cost, global index) of the cheapest candidate.  With one GPU it is a 1-rank communicator."""
+    lib = os.path.join(ROOT, "fast_racing_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "argmin_nccl")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tests", "cpp", "argmin_nccl.cpp"), "-L", lib, "-lfrx", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lnccl",
+           "-pthread", f"-Wl,-rpath,{lib}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all ranks agree" in r.stdout, r.stdout + r.stderr
+
+
 def test_trajectory_containers_cpu():
     """Piece / Trajectory helpers the planner calls downstream: exact max velocity / acceleration rates
     (root isolation instead of root_finder.hpp) against 2e5-point sampling, checkMax*Rate, getRotation, normalised
