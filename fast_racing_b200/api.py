@@ -161,6 +161,11 @@ def load_library():
         "frx_batch_profile_eval": (ci, [vp, vp, vp, vp, vp, ci, P(cd)]),
         "frx_batch_penalty_launch": (ci, [vp, P(C.c_longlong)]),
         "frx_measure_fp64_tflops": (cd, []),
+        "frx_corridor_dilate": (ci, [P(cd), ci, P(cd), P(cd), P(cd), P(cd), ci, P(cd)]),
+        "frx_corridor_generate": (ci, [P(cd), ci, P(cd), ci, P(cd), cd, vp, vp, P(ci), P(cd), ci, ci, P(ci)]),
+        "frx_cloud_create": (ci, [P(cd), ci, ci, P(vp)]),
+        "frx_cloud_destroy": (None, [vp]),
+        "frx_cloud_dilate_batch": (ci, [vp, P(cd), ci, P(cd), P(ci), P(cd), P(cd)]),
         "frx_device_numa_node": (ci, [ci]),
         "frx_bind_thread_to_device": (ci, [ci]),
     }
@@ -177,7 +182,8 @@ EXPORTED_SYMBOLS = [
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
     "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_batch_set_reference_order", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version", "frx_device_numa_node", "frx_bind_thread_to_device",
-    "frx_batch_argmin_allgather",
+    "frx_batch_argmin_allgather", "frx_corridor_dilate", "frx_corridor_generate", "frx_cloud_create", "frx_cloud_destroy",
+    "frx_cloud_dilate_batch",
 ]
 
 
@@ -230,6 +236,74 @@ def enumerate_vertices(faces):
     if v < 0:
         raise FrxError(v, "frx_enumerate_vertices")
     return out[: 3 * v].reshape(v, 3).copy()
+
+
+CORRIDOR_MAX_FACES = 96
+IS_BLOCKED_T = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def corridor_dilate(obs, p1, p2, bbox):
+    """LineSegment3D::dilate for one segment on the host: (faces F x 6 as (n, p), ellipsoid C 3x3, d)."""
+    lib = load_library()
+    obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
+    p1, p2, bbox = (np.ascontiguousarray(v, dtype=np.float64) for v in (p1, p2, bbox))
+    faces = np.zeros(6 * 512)
+    ell = np.zeros(12)
+    F = lib.frx_corridor_dilate(_dp(obs), len(obs) // 3, _dp(p1), _dp(p2), _dp(bbox), _dp(faces), 512, _dp(ell))
+    if F < 0:
+        raise FrxError(F, "frx_corridor_dilate")
+    return faces[: 6 * F].reshape(F, 6).copy(), ell[:9].reshape(3, 3).copy(), ell[9:].copy()
+
+
+def corridor_generate(obs, path, bbox, map_height, blocked=None):
+    """The walk of MavGlobalPlanner::plan along `path` (host): returns (face_off, faces F x 6); blocked(a, b) -> bool or None."""
+    lib = load_library()
+    obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
+    path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1)
+    bbox = np.ascontiguousarray(bbox, dtype=np.float64)
+    cap_poly, cap_faces = len(path) // 3 + 1, (len(path) // 3 + 1) * CORRIDOR_MAX_FACES
+    off = np.zeros(cap_poly + 1, np.int32)
+    faces = np.zeros(6 * cap_faces)
+    n = C.c_int()
+    cb = IS_BLOCKED_T(lambda ctx, a, b: int(bool(blocked(np.array(a[:3]), np.array(b[:3]))))) if blocked else None
+    st = lib.frx_corridor_generate(_dp(obs), len(obs) // 3, _dp(path), len(path) // 3, _dp(bbox), map_height,
+                                   C.cast(cb, C.c_void_p) if cb else None, None, _ip(off), _dp(faces), cap_poly, cap_faces, C.byref(n))
+    _check(st, "frx_corridor_generate")
+    off = off[: n.value + 1].copy()
+    return off, faces[: 6 * off[-1]].reshape(-1, 6).copy()
+
+
+class Cloud:
+    """An obstacle cloud resident on one GPU (frx_cloud): the segment step of the corridor generation, batched."""
+
+    def __init__(self, obs, device=-1):
+        self.lib = load_library()
+        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(-1)
+        h = C.c_void_p()
+        _check(self.lib.frx_cloud_create(_dp(obs), len(obs) // 3, device, C.byref(h)), "frx_cloud_create")
+        self.h = h
+
+    def dilate_batch(self, segments, bbox):
+        seg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 6)
+        bbox = np.ascontiguousarray(bbox, dtype=np.float64)
+        n = len(seg)
+        cnt = np.zeros(n, np.int32)
+        faces = np.zeros(n * CORRIDOR_MAX_FACES * 6)
+        ell = np.zeros(12 * n)
+        _check(self.lib.frx_cloud_dilate_batch(self.h, _dp(seg.reshape(-1)), n, _dp(bbox), _ip(cnt), _dp(faces), _dp(ell)), "frx_cloud_dilate_batch")
+        faces = faces.reshape(n, CORRIDOR_MAX_FACES, 6)
+        return [faces[i, : max(cnt[i], 0)].copy() for i in range(n)], cnt, ell.reshape(n, 12)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.frx_cloud_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:

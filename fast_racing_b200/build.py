@@ -27,6 +27,8 @@ UNITS = [
     ("geometry_kernels.cu", "", ["--fmad=false"]),  # bit-identical to the host enumeration (host_geometry.cpp)
     ("host_model.cpp", "", []),
     ("host_geometry.cpp", "", []),
+    ("corridor.cpp", "", []),
+    ("corridor_kernels.cu", "", ["--fmad=false"]),  # same point selection as the host path (corridor.cpp)
     ("eval_kernels.cu", "_exact", ["-DFRX_EXACT=1", "--fmad=false"]),
     ("solver.cu", "_exact", ["-DFRX_EXACT=1", "--fmad=false"]),
 ]

@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "../../include/frx.h"
+#include "corridor.hpp"
+#include "corridor_kernels.cuh"
 #include "device_batch.cuh"
 #include "geometry_kernels.cuh"
 #include "host_model.hpp"
@@ -285,6 +287,89 @@ static int device_geometry(const frx_problem* problems, int count, DeviceGeometr
 }
 
 extern "C" {
+
+// ---- corridor generation -----------------------------------------------------------------------------
+int frx_corridor_dilate(const double* obs, int n_obs, const double* p1, const double* p2, const double* bbox, double* faces, int cap_faces,
+                        double* ellipsoid12) {
+    if ((n_obs > 0 && !obs) || n_obs < 0 || !p1 || !p2 || !bbox || !faces) return FRX_ERR_INVALID_ARG;
+    std::vector<double> f;
+    const int F = dilate_segment(obs, n_obs, p1, p2, bbox, f, ellipsoid12);
+    if (F > cap_faces) return FRX_ERR_CAPACITY;
+    std::copy(f.begin(), f.end(), faces);
+    return F;
+}
+int frx_corridor_generate(const double* obs, int n_obs, const double* path, int n_path, const double* bbox, double map_height,
+                          frx_is_blocked_t blocked, void* ctx, int* face_off, double* faces, int cap_poly, int cap_faces, int* n_poly) {
+    if ((n_obs > 0 && !obs) || n_obs < 0 || !path || n_path < 2 || !bbox || !face_off || !faces || !n_poly) return FRX_ERR_INVALID_ARG;
+    std::vector<int> off;
+    std::vector<double> f;
+    const int P = generate_corridor(obs, n_obs, path, n_path, bbox, map_height, blocked, ctx, off, f);
+    if (P > cap_poly || (int)f.size() / 6 > cap_faces) return FRX_ERR_CAPACITY;
+    std::copy(off.begin(), off.end(), face_off);
+    std::copy(f.begin(), f.end(), faces);
+    *n_poly = P;
+    return FRX_OK;
+}
+}  // extern "C"
+struct frx_cloud {
+    int device = 0, n = 0;
+    double* obs = nullptr;
+};
+extern "C" {
+int frx_cloud_create(const double* obs, int n_obs, int device_ordinal, frx_cloud** out) {
+    if (!obs || n_obs < 1 || !out) return FRX_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        std::fprintf(stderr, "[frx] no CUDA device: this library has no CPU fallback\n");
+        return FRX_ERR_CUDA;
+    }
+    frx_cloud* c = new (std::nothrow) frx_cloud();
+    if (!c) return FRX_ERR_NOMEM;
+    c->n = n_obs;
+    if (device_ordinal < 0) {
+        if (cudaGetDevice(&c->device) != cudaSuccess) {
+            delete c;
+            return FRX_ERR_CUDA;
+        }
+    } else
+        c->device = device_ordinal;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&c->obs, sizeof(double) * 3 * (size_t)n_obs) != cudaSuccess ||
+        cudaMemcpy(c->obs, obs, sizeof(double) * 3 * (size_t)n_obs, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (c->obs) cudaFree(c->obs);
+        delete c;
+        return cuda_fail(cudaGetLastError(), "frx_cloud_create");
+    }
+    *out = c;
+    return FRX_OK;
+}
+void frx_cloud_destroy(frx_cloud* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->obs) cudaFree(c->obs);
+    delete c;
+}
+int frx_cloud_dilate_batch(frx_cloud* c, const double* segments, int n_seg, const double* bbox, int* face_cnt, double* faces, double* ellipsoids) {
+    if (!c || !segments || n_seg < 1 || !bbox || !face_cnt || !faces) return FRX_ERR_INVALID_ARG;
+    CK(cudaSetDevice(c->device));
+    double *d_seg = nullptr, *d_faces = nullptr, *d_ell = nullptr;
+    int *d_idx = nullptr, *d_cnt = nullptr;
+    unsigned char *d_alive = nullptr, *d_in0 = nullptr;
+    const size_t nf = (size_t)n_seg * FRX_CORRIDOR_MAX_FACES * 6;
+    bool ok = cudaMalloc(&d_seg, sizeof(double) * 6 * (size_t)n_seg) == cudaSuccess && cudaMalloc(&d_faces, sizeof(double) * nf) == cudaSuccess &&
+              cudaMalloc(&d_ell, sizeof(double) * 12 * (size_t)n_seg) == cudaSuccess && cudaMalloc(&d_cnt, sizeof(int) * n_seg) == cudaSuccess &&
+              cudaMalloc(&d_idx, sizeof(int) * (size_t)n_seg * c->n) == cudaSuccess && cudaMalloc(&d_alive, (size_t)n_seg * c->n) == cudaSuccess &&
+              cudaMalloc(&d_in0, (size_t)n_seg * c->n) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_seg, segments, sizeof(double) * 6 * (size_t)n_seg, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && frx::launch_dilate_batch(c->obs, c->n, d_seg, n_seg, bbox, d_idx, d_alive, d_in0, d_cnt, d_faces, d_ell, nullptr) == cudaSuccess;
+    ok = ok && cudaMemcpy(face_cnt, d_cnt, sizeof(int) * n_seg, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(faces, d_faces, sizeof(double) * nf, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && ellipsoids) ok = cudaMemcpy(ellipsoids, d_ell, sizeof(double) * 12 * (size_t)n_seg, cudaMemcpyDeviceToHost) == cudaSuccess;
+    const cudaError_t err = ok ? cudaSuccess : cudaGetLastError();
+    cudaFree(d_seg), cudaFree(d_faces), cudaFree(d_ell), cudaFree(d_cnt), cudaFree(d_idx), cudaFree(d_alive), cudaFree(d_in0);
+    if (!ok) return cuda_fail(err, "frx_cloud_dilate_batch");
+    return FRX_OK;
+}
 
 int frx_device_numa_node(int device_ordinal) { return device_numa_node(device_ordinal); }
 

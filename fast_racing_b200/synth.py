@@ -92,6 +92,33 @@ def perturb_track(base_centres, seed, sigma=0.25):
     return c
 
 
+def obstacle_cloud(seed, centres, n_points=20000, clearance=0.7, margin=5.0, z_range=(0.0, 3.0)):
+    """A random obstacle cloud around a path that leaves a tube of radius `clearance` around the poly-line free: the kind of
+    input MavGlobalPlanner::plan hands to EllipsoidDecomp3D::set_obs (MinCoPlan_CPU.cpp:38), for the corridor-generation tests."""
+    rng = np.random.default_rng(seed)
+    c = np.asarray(centres, dtype=float)
+    lo = np.r_[c[:, :2].min(0) - margin, z_range[0]]
+    hi = np.r_[c[:, :2].max(0) + margin, z_range[1]]
+    pts = rng.uniform(lo, hi, size=(n_points, 3))
+    dmin = np.full(len(pts), np.inf)
+    for a, b in zip(c[:-1], c[1:]):
+        d = b - a
+        t = np.clip(((pts - a) @ d) / (d @ d), 0.0, 1.0)
+        dmin = np.minimum(dmin, np.linalg.norm(pts - (a + t[:, None] * d), axis=1))
+    return np.ascontiguousarray(pts[dmin > clearance])
+
+
+def sample_path(centres, spacing=0.25):
+    """Densely sampled poly-line through the centres (what the front end's getSamplePath returns, MinCoPlan_CPU.cpp:19-35)."""
+    c = np.asarray(centres, dtype=float)
+    out = [c[0]]
+    for a, b in zip(c[:-1], c[1:]):
+        n = max(1, int(np.ceil(np.linalg.norm(b - a) / spacing)))
+        for k in range(1, n + 1):
+            out.append(a + (b - a) * k / n)
+    return np.array(out)
+
+
 CONFIGS = {
     # BASELINE.json configs[0..4] (SURVEY.md §8d); B is the full-size batch, tests use fewer.
     "C1": dict(n_poly=8, n_faces=10, itg_spaces=48, params=ZHANGJIAJIE, chi=(0.0, 1.0e4, 1.0e4, 1.0e4), B=1),

@@ -150,6 +150,32 @@ int frx_batch_set_reference_order(frx_batch *b, int on);
 /* Device-time (ms, CUDA events on the batch stream) of the last eval / optimize call. */
 double frx_batch_last_ms(const frx_batch *b);
 
+/* ---- corridor generation: the step BEFORE setup() in MavGlobalPlanner::plan (MinCoPlan_CPU.cpp:37-105) ----
+ * obstacle cloud: 3 doubles per point (the planner's *obs_pointer); path: 3 doubles per point (the front end's sample path);
+ * bbox: config.polyhedronBox; a polytope comes back as (n, p) rows = the columns of the reference's 6 x F hPolys matrices. */
+#define FRX_CORRIDOR_MAX_FACES 96 /* faces of one polytope (obstacle-tangent planes + 6 box planes + ceiling/floor) */
+/* map_util->isBlocked(a, b) of the front end (out of scope here): non-zero when the straight line a -> b is blocked. */
+typedef int (*frx_is_blocked_t)(void *ctx, const double *a, const double *b);
+/* LineSegment3D::dilate(0) (decomp_util/line_segment.h:33-37) for one segment, on the host: obstacle-tangent planes in the
+ * order they are found, then the six local bounding-box planes.  Returns the number of faces (< 0: FRX_ERR_*).
+ * ellipsoid12 (may be NULL): C row-major 3x3, then the centre d. */
+int frx_corridor_dilate(const double *obs, int n_obs, const double *p1, const double *p2, const double *bbox, double *faces,
+                        int cap_faces, double *ellipsoid12);
+/* The whole walk along the path with the ceiling / floor planes added (MinCoPlan_CPU.cpp:44-91), on the host.  face_off
+ * receives *n_poly + 1 offsets.  `blocked` may be NULL (nothing is blocked: only the 4 m rule cuts the segments). */
+int frx_corridor_generate(const double *obs, int n_obs, const double *path, int n_path, const double *bbox, double map_height,
+                          frx_is_blocked_t blocked, void *ctx, int *face_off, double *faces, int cap_poly, int cap_faces,
+                          int *n_poly);
+/* The obstacle cloud resident on one GPU, and the segment step batched over many segments (one CTA per segment): what a
+ * planner that grows the corridors of many candidate paths at once calls per walk step. */
+typedef struct frx_cloud frx_cloud;
+int frx_cloud_create(const double *obs, int n_obs, int device_ordinal, frx_cloud **out);
+void frx_cloud_destroy(frx_cloud *c);
+/* segments: 6 doubles each (p1, p2); face_cnt[n_seg]; faces[n_seg][FRX_CORRIDOR_MAX_FACES][6]; ellipsoids (may be NULL):
+ * 12 per segment.  face_cnt < 0 for a segment whose polytope would exceed FRX_CORRIDOR_MAX_FACES. */
+int frx_cloud_dilate_batch(frx_cloud *c, const double *segments, int n_seg, const double *bbox, int *face_cnt, double *faces,
+                           double *ellipsoids);
+
 /* One process (or thread) per GPU: NUMA node of the GPU (-1 = unknown), and "move the calling thread and the threads it
  * creates later to that node's CPUs and prefer its memory" — call it first in each rank of a multi-GPU job.  The batch's
  * pinned host buffers are placed on the GPU's node regardless (FRX_NUMA=0 disables both).  The reference is a single

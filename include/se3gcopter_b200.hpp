@@ -363,6 +363,63 @@ public:
 #endif
 };
 
+// ---- corridor generation: the EllipsoidDecomp3D surface MavGlobalPlanner::plan uses (MinCoPlan_CPU.cpp:37-63) -----------
+// decomp_util/ellipsoid_decomp.h:32-36,58-80 (set_obs, set_local_bbox, dilate, get_polyhedrons, get_ellipsoids) and
+// decomp_geometry/polyhedron.h (Hyperplane3D, Polyhedron3D::add / inside / hyperplanes) on plain arrays.
+typedef std::array<double, 3> Vec3f;
+struct Hyperplane3D {
+    Vec3f p_, n_;
+    Hyperplane3D() {}
+    Hyperplane3D(const Vec3f& p, const Vec3f& n) : p_(p), n_(n) {}
+    double signed_dist(const Vec3f& pt) const { return n_[0] * (pt[0] - p_[0]) + n_[1] * (pt[1] - p_[1]) + n_[2] * (pt[2] - p_[2]); }
+};
+struct Polyhedron3D {
+    std::vector<Hyperplane3D> vs_;
+    void add(const Hyperplane3D& v) { vs_.push_back(v); }
+    bool inside(const Vec3f& pt) const {
+        for (const auto& v : vs_)
+            if (v.signed_dist(pt) > 1e-10) return false;  // epsilon_ of decomp_basis/data_type.h:127
+        return true;
+    }
+    const std::vector<Hyperplane3D>& hyperplanes() const { return vs_; }
+};
+struct Ellipsoid3D {
+    double C_[9];  // row-major
+    Vec3f d_;
+};
+class EllipsoidDecomp3D {
+    std::vector<double> obs_;
+    double bbox_[3] = {0, 0, 0};
+    std::vector<Polyhedron3D> polyhedrons_;
+    std::vector<Ellipsoid3D> ellipsoids_;
+
+public:
+    void set_obs(const std::vector<Vec3f>& obs) {
+        obs_.clear();
+        for (const auto& o : obs) obs_.insert(obs_.end(), o.begin(), o.end());
+    }
+    void set_local_bbox(const Vec3f& bbox) { bbox_[0] = bbox[0], bbox_[1] = bbox[1], bbox_[2] = bbox[2]; }
+    // one polytope + ellipsoid per path segment, as ellipsoid_decomp.h:64-80
+    void dilate(const std::vector<Vec3f>& path, double /*offset_x*/ = 0) {
+        polyhedrons_.clear(), ellipsoids_.clear();
+        std::vector<double> faces(6 * 512);
+        for (size_t i = 0; i + 1 < path.size(); i++) {
+            Ellipsoid3D e;
+            double ell[12];
+            const int F = frx_corridor_dilate(obs_.data(), (int)obs_.size() / 3, path[i].data(), path[i + 1].data(), bbox_, faces.data(), 512, ell);
+            if (F < 0) throw std::runtime_error(std::string("EllipsoidDecomp3D::dilate: ") + frx_strerror(F));
+            Polyhedron3D poly;
+            for (int k = 0; k < F; k++)
+                poly.add(Hyperplane3D({faces[6 * k + 3], faces[6 * k + 4], faces[6 * k + 5]}, {faces[6 * k], faces[6 * k + 1], faces[6 * k + 2]}));
+            for (int k = 0; k < 9; k++) e.C_[k] = ell[k];
+            e.d_ = {ell[9], ell[10], ell[11]};
+            polyhedrons_.push_back(poly), ellipsoids_.push_back(e);
+        }
+    }
+    const std::vector<Polyhedron3D>& get_polyhedrons() const { return polyhedrons_; }
+    const std::vector<Ellipsoid3D>& get_ellipsoids() const { return ellipsoids_; }
+};
+
 // ---- batch of candidate trajectories (extension) ----------------------------------------------------
 class SE3GCOPTERBatch {
     frx_batch* h = nullptr;

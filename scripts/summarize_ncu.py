@@ -51,14 +51,16 @@ for r in cols:
 json.dump(out, open(tag + "_dram_traffic.json", "w"), indent=1)
 ops = {}
 for op in ("dfma", "dmul", "dadd"):
-    name = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum"
+    name = f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"
     ops[op] = hdr.index(name) if name in hdr else None
-if all(v is not None for v in ops.values()):
-    for r in cols:
+icyc = hdr.index("smsp__cycles_elapsed.avg") if "smsp__cycles_elapsed.avg" in hdr else None
+if icyc is not None and all(v is not None for v in ops.values()):
+    for r in cols:  # thread instructions of the launch = (sum over SMSPs per elapsed cycle) x elapsed cycles
         k = out["kernels"][short(r[ki])]
+        cyc = float(r[icyc].replace(",", ""))
         for op, i in ops.items():
-            k[op] = float(r[i].replace(",", ""))
+            k[op] = float(r[i].replace(",", "")) * cyc
         k["flops"] = 2.0 * k["dfma"] + k["dmul"] + k["dadd"]
+        k["cycles_elapsed"] = cyc
     out["shape"] = shape
     json.dump(out, open(tag + "_ncu_eval.json", "w"), indent=1)
-print(open(tag + "_ncu_full_eval.csv").read())

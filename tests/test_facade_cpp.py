@@ -68,6 +68,19 @@ def test_c_abi_cross_rank_argmin_nccl():
     assert r.returncode == 0 and "all ranks agree" in r.stdout, r.stdout + r.stderr
 
 
+def test_facade_corridor_generation_cpu():
+    """SURVEY §8(f-4): the corridor half of MavGlobalPlanner::plan written against frx::EllipsoidDecomp3D / Polyhedron3D with the
+    reference's own call sequence (MinCoPlan_CPU.cpp:37-105): polytopes cover the path ends, no obstacle point is strictly inside."""
+    lib = os.path.join(ROOT, "fast_racing_b200")
+    exe = os.path.join(ROOT, "tests", "cpp", "facade_corridor")
+    cmd = ["g++", "-std=c++14", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_corridor.cpp"),
+           "-L", lib, "-lfrx", f"-Wl,-rpath,{lib}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_trajectory_containers_cpu():
     """Piece / Trajectory helpers the planner calls downstream: exact max velocity / acceleration rates
     (root isolation instead of root_finder.hpp) against 2e5-point sampling, checkMax*Rate, getRotation, normalised
