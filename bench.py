@@ -330,7 +330,9 @@ def load_profile_json(name):
 
 def solve_leg(cx, api, probs, tol, first_global, label):
     """Batched L-BFGS solves of `probs` on this rank + the cross-rank arg-min.  Returns the record (rank-agnostic values)."""
+    t_c = time.perf_counter()
     sbatch = api.Batch(probs, device=cx.local_rank)
+    create_ms = (time.perf_counter() - t_c) * 1e3  # V-polytope extraction (device), tables, packing, uploads
     sb = sbatch.count
     cx.sync_all()
     t0 = time.perf_counter()
@@ -340,6 +342,7 @@ def solve_leg(cx, api, probs, tol, first_global, label):
     best_c, best_i, gather_ms = cx.argmin_gather(bc, first_global + bi)
     wall_max = cx.max_over_ranks([wall])[0]
     rec = {"workload": label, "value": sb * cx.world / wall_max, "unit": "solves/s", "batch_per_gpu": sb, "rel_tol": tol,
+           "batch_create_ms": create_ms,
            "wall_s_max_over_ranks": wall_max, "device_ms": r["device_ms"], "ticks": int(r["ticks"]),
            "iterations_mean": float(r["iterations"].mean()), "evaluations_mean": float(r["evaluations"].mean()),
            "evaluations_max": int(r["evaluations"].max()),
@@ -356,6 +359,28 @@ def solve_leg(cx, api, probs, tol, first_global, label):
                                 "achieved_GBps": uk["history_bytes"] / (uk["device_ms"] * 1e-3) / 1e9}
     sbatch.close()
     return rec
+
+
+def corridor_leg(cx, api, synth, n_points=200000, n_seg=64):
+    """Row f-4: the segment step of the corridor generation, batched on the device, beside the host path (one thread)."""
+    rng = np.random.default_rng(3)
+    centres = synth.corridor_centres(rng, n_seg)
+    obs = synth.obstacle_cloud(3, centres, n_points, margin=8.0)
+    segs = np.array([np.r_[a, b] for a, b in zip(centres[:-1], centres[1:])])
+    bbox = np.array([4.0, 4.0, 2.5])
+    cloud = api.Cloud(obs, device=cx.local_rank)
+    cloud.dilate_batch(segs[:2], bbox)
+    t0 = time.perf_counter()
+    _, cnt, _ = cloud.dilate_batch(segs, bbox)
+    dev_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    for sg in segs[:8]:
+        api.corridor_dilate(obs, sg[:3], sg[3:], bbox)
+    host_ms = (time.perf_counter() - t0) * 1e3 / 8
+    cloud.close()
+    return {"workload": f"{len(segs)} path segments against an obstacle cloud of {len(obs)} points (LineSegment3D::dilate each)",
+            "device_batch_ms": dev_ms, "device_us_per_segment": dev_ms * 1e3 / len(segs), "host_ms_per_segment_1_thread": host_ms,
+            "faces_per_segment_mean": float(cnt.mean()), "note": "device time includes the H2D of the segments and the D2H of the faces"}
 
 
 def single_solve_latency(cx, api, name, tol):
@@ -521,6 +546,7 @@ def main():
             if not a.no_cpu_baseline:
                 cfgs["C1"] = single_solve_latency(cx, api, "C1", 1e-6)
                 cfgs["C2"] = single_solve_latency(cx, api, "C2", 1e-6)
+            cfgs["corridor"] = corridor_leg(cx, api, synth)
         extras["configs"] = cfgs
 
     if rank == 0:

@@ -166,6 +166,7 @@ def load_library():
         "frx_cloud_create": (ci, [P(cd), ci, ci, P(vp)]),
         "frx_cloud_destroy": (None, [vp]),
         "frx_cloud_dilate_batch": (ci, [vp, P(cd), ci, P(cd), P(ci), P(cd), P(cd)]),
+        "frx_cloud_generate_batch": (ci, [vp, P(cd), P(ci), ci, P(cd), cd, vp, vp, P(ci), P(ci), P(cd), ci, ci]),
         "frx_device_numa_node": (ci, [ci]),
         "frx_bind_thread_to_device": (ci, [ci]),
     }
@@ -183,7 +184,7 @@ EXPORTED_SYMBOLS = [
     "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_batch_set_reference_order", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version", "frx_device_numa_node", "frx_bind_thread_to_device",
     "frx_batch_argmin_allgather", "frx_corridor_dilate", "frx_corridor_generate", "frx_cloud_create", "frx_cloud_destroy",
-    "frx_cloud_dilate_batch",
+    "frx_cloud_dilate_batch", "frx_cloud_generate_batch",
 ]
 
 
@@ -293,6 +294,26 @@ class Cloud:
         _check(self.lib.frx_cloud_dilate_batch(self.h, _dp(seg.reshape(-1)), n, _dp(bbox), _ip(cnt), _dp(faces), _dp(ell)), "frx_cloud_dilate_batch")
         faces = faces.reshape(n, CORRIDOR_MAX_FACES, 6)
         return [faces[i, : max(cnt[i], 0)].copy() for i in range(n)], cnt, ell.reshape(n, 12)
+
+    def generate_batch(self, paths, bbox, map_height):
+        """Corridors of many candidate paths at once (lock-step walks, one batched device step per walk step):
+        returns a list of (face_off, faces F x 6) per path."""
+        bbox = np.ascontiguousarray(bbox, dtype=np.float64)
+        poff = np.zeros(len(paths) + 1, np.int32)
+        for i, p in enumerate(paths):
+            poff[i + 1] = poff[i] + len(p)
+        flat = np.ascontiguousarray(np.vstack(paths), dtype=np.float64).reshape(-1)
+        cap_poly, cap_faces = int(poff[-1]), int(poff[-1]) * CORRIDOR_MAX_FACES
+        poly_off = np.zeros(len(paths) + 1, np.int32)
+        face_off = np.zeros(cap_poly + 1, np.int32)
+        faces = np.zeros(6 * cap_faces)
+        _check(self.lib.frx_cloud_generate_batch(self.h, _dp(flat), _ip(poff), len(paths), _dp(bbox), map_height, None, None, _ip(poly_off),
+                                                 _ip(face_off), _dp(faces), cap_poly, cap_faces), "frx_cloud_generate_batch")
+        out = []
+        for i in range(len(paths)):
+            fo = face_off[poly_off[i]:poly_off[i + 1] + 1]
+            out.append((fo - fo[0], faces[6 * fo[0]:6 * fo[-1]].reshape(-1, 6).copy()))
+        return out
 
     def close(self):
         if getattr(self, "h", None):

@@ -121,7 +121,7 @@ int generate_corridor(const double* obs, int n_obs, const double* path, int n_pa
         faces.insert(faces.end(), f.begin(), f.end());
         face_off.push_back(face_off.back() + F + 2);
         if (next < 0) break;
-        i = next;
+        i = next > i ? next : i + 1;  // the reference's advance rule can stall (wp == i, an endless loop there): move on
     }
     return (int)face_off.size() - 1;
 }

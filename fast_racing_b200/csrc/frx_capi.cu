@@ -371,6 +371,61 @@ int frx_cloud_dilate_batch(frx_cloud* c, const double* segments, int n_seg, cons
     return FRX_OK;
 }
 
+int frx_cloud_generate_batch(frx_cloud* c, const double* paths, const int* path_off, int n_paths, const double* bbox, double map_height,
+                             frx_is_blocked_t blocked, void* ctx, int* poly_off, int* face_off, double* faces, int cap_poly, int cap_faces) {
+    if (!c || !paths || !path_off || n_paths < 1 || !bbox || !poly_off || !face_off || !faces) return FRX_ERR_INVALID_ARG;
+    std::vector<int> cur(n_paths, 0), k_of(n_paths, 0);
+    std::vector<char> walking(n_paths, 1);
+    std::vector<std::vector<int>> offs(n_paths, std::vector<int>(1, 0));
+    std::vector<std::vector<double>> fcs(n_paths);
+    std::vector<double> seg, out((size_t)n_paths * FRX_CORRIDOR_MAX_FACES * 6);
+    std::vector<int> who, cnt(n_paths);
+    for (int p = 0; p < n_paths; p++) walking[p] = path_off[p + 1] - path_off[p] >= 2;
+    for (;;) {
+        seg.clear(), who.clear();
+        for (int p = 0; p < n_paths; p++) {
+            if (!walking[p]) continue;
+            const double* path = paths + 3 * (size_t)path_off[p];
+            const int np = path_off[p + 1] - path_off[p];
+            k_of[p] = corridor_walk_target(path, np, cur[p], blocked, ctx, 4.0);
+            seg.insert(seg.end(), path + 3 * (size_t)cur[p], path + 3 * (size_t)cur[p] + 3);
+            seg.insert(seg.end(), path + 3 * (size_t)k_of[p], path + 3 * (size_t)k_of[p] + 3);
+            who.push_back(p);
+        }
+        if (who.empty()) break;
+        const int s = frx_cloud_dilate_batch(c, seg.data(), (int)who.size(), bbox, cnt.data(), out.data(), nullptr);
+        if (s != FRX_OK) return s;
+        for (size_t q = 0; q < who.size(); q++) {
+            const int p = who[q];
+            if (cnt[q] < 0) return FRX_ERR_CAPACITY;
+            const double* f = &out[q * FRX_CORRIDOR_MAX_FACES * 6];
+            const double* path = paths + 3 * (size_t)path_off[p];
+            const int np = path_off[p + 1] - path_off[p];
+            int next = corridor_walk_advance(path, np, cur[p], k_of[p], f, cnt[q]);
+            fcs[p].insert(fcs[p].end(), f, f + 6 * (size_t)cnt[q]);
+            const double ceil_floor[12] = {0, 0, 1, 0, 0, map_height, 0, 0, -1, 0, 0, 0};  // MinCoPlan_CPU.cpp:85-91
+            fcs[p].insert(fcs[p].end(), ceil_floor, ceil_floor + 12);
+            offs[p].push_back(offs[p].back() + cnt[q] + 2);
+            if (next >= 0 && next <= cur[p]) next = cur[p] + 1;  // the reference's advance rule can stall (wp == i): move on
+            if (next < 0 || next >= np - 1)
+                walking[p] = 0;
+            else
+                cur[p] = next;
+        }
+    }
+    int P = 0, F = 0;
+    poly_off[0] = 0, face_off[0] = 0;
+    for (int p = 0; p < n_paths; p++) {
+        const int np = (int)offs[p].size() - 1;
+        if (P + np > cap_poly || F + offs[p].back() > cap_faces) return FRX_ERR_CAPACITY;
+        for (int k = 0; k < np; k++) face_off[P + k + 1] = F + offs[p][k + 1];
+        std::copy(fcs[p].begin(), fcs[p].end(), faces + 6 * (size_t)F);
+        P += np, F += offs[p].back();
+        poly_off[p + 1] = P;
+    }
+    return FRX_OK;
+}
+
 int frx_device_numa_node(int device_ordinal) { return device_numa_node(device_ordinal); }
 
 // Moves the CALLING thread (and the threads it creates later) to the CPUs of the GPU's NUMA node and makes that node the

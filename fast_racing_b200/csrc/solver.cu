@@ -743,23 +743,58 @@ int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, const EvalFn& 
     s->n_samples = 0;
     if (cudaMemsetAsync(sv.hist_bytes, 0, sizeof(unsigned long long), io.stream) != cudaSuccess) return FRX_ERR_CUDA;
     if (cudaMemsetAsync(sv.dir_err_bits, 0, sizeof(unsigned long long), io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-    while (n_active > 0 && ticks < io.max_ticks) {
-        for (int t = 0; t < io.poll_every; t++) {
-            if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-            const bool sample = (t == 0);
-            if (sample) {
-                if ((int)s->ev.size() < 2 * (s->n_samples + 1)) {
-                    cudaEvent_t a, b2;
-                    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b2) != cudaSuccess) return FRX_ERR_CUDA;
-                    s->ev.push_back(a), s->ev.push_back(b2);
-                }
-                cudaEventRecord(s->ev[2 * s->n_samples], io.stream);
-            }
-            sv.count_bytes = sample ? 1 : 0;
-            if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-            if (sample) cudaEventRecord(s->ev[2 * s->n_samples + 1], io.stream), s->n_samples++;
-            ticks++;
+    // A tick is four launches of a few microseconds to a few hundred each; a poll group (poll_every ticks = 4 * poll_every
+    // launches with identical arguments) is captured ONCE into a CUDA graph and replayed, so the host pays one launch per group
+    // and the device sees no inter-kernel launch gaps — what matters when few trajectories are still alive (or B = 1, the
+    // reference's own call).  Every GRAPH_SAMPLE_EVERY-th group runs un-captured with the first update launch bracketed by
+    // events and counting its history bytes (-> bench.py "solves.update_kernel").  FRX_SOLVER_GRAPH=0 disables the capture.
+    constexpr int GRAPH_SAMPLE_EVERY = 8;
+    bool use_graph = true;
+    if (const char* e = getenv("FRX_SOLVER_GRAPH")) use_graph = !(e[0] == '0');
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    struct GraphGuard {
+        cudaGraph_t& g;
+        cudaGraphExec_t& e;
+        ~GraphGuard() {
+            if (e) cudaGraphExecDestroy(e);
+            if (g) cudaGraphDestroy(g);
         }
+    } gguard{graph, gexec};
+    int group = 0;
+    while (n_active > 0 && ticks < io.max_ticks) {
+        const bool sampled_group = !use_graph || (group % GRAPH_SAMPLE_EVERY == 0);
+        if (sampled_group) {
+            for (int t = 0; t < io.poll_every; t++) {
+                if (eval(sv.x, sv.cost, sv.g, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+                const bool sample = (t == 0);
+                if (sample) {
+                    if ((int)s->ev.size() < 2 * (s->n_samples + 1)) {
+                        cudaEvent_t a, b2;
+                        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b2) != cudaSuccess) return FRX_ERR_CUDA;
+                        s->ev.push_back(a), s->ev.push_back(b2);
+                    }
+                    cudaEventRecord(s->ev[2 * s->n_samples], io.stream);
+                }
+                sv.count_bytes = sample ? 1 : 0;
+                if (solver_launch_update(s, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+                if (sample) cudaEventRecord(s->ev[2 * s->n_samples + 1], io.stream), s->n_samples++;
+                ticks++;
+            }
+        } else {
+            if (!gexec) {
+                sv.count_bytes = 0;
+                if (cudaStreamBeginCapture(io.stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return FRX_ERR_CUDA;
+                bool ok = true;
+                for (int t = 0; t < io.poll_every && ok; t++)
+                    ok = eval(sv.x, sv.cost, sv.g, io.stream) == cudaSuccess && solver_launch_update(s, io.stream) == cudaSuccess;
+                const cudaError_t ce = cudaStreamEndCapture(io.stream, &graph);
+                if (!ok || ce != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) return FRX_ERR_CUDA;
+            }
+            if (cudaGraphLaunch(gexec, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
+            ticks += io.poll_every;
+        }
+        group++;
         r = solver_poll_active(s, io.stream, &n_active);
         if (r != FRX_OK) return r;
     }

@@ -176,6 +176,13 @@ void frx_cloud_destroy(frx_cloud *c);
 int frx_cloud_dilate_batch(frx_cloud *c, const double *segments, int n_seg, const double *bbox, int *face_cnt, double *faces,
                            double *ellipsoids);
 
+/* The walk of MavGlobalPlanner::plan for MANY candidate paths at once (e.g. the distinct corridor topologies of one planning
+ * cycle): all walks advance in lock-step, every step is ONE frx_cloud_dilate_batch over the paths still walking.
+ * path_off[n_paths + 1] offsets (in points) into paths[3 * total]; poly_off[n_paths + 1] receives offsets (in polytopes) into
+ * face_off[total_polys + 1] (offsets in faces) into faces.  `blocked` (may be NULL) is called as blocked(ctx, a, b). */
+int frx_cloud_generate_batch(frx_cloud *c, const double *paths, const int *path_off, int n_paths, const double *bbox, double map_height,
+                             frx_is_blocked_t blocked, void *ctx, int *poly_off, int *face_off, double *faces, int cap_poly, int cap_faces);
+
 /* One process (or thread) per GPU: NUMA node of the GPU (-1 = unknown), and "move the calling thread and the threads it
  * creates later to that node's CPUs and prefer its memory" — call it first in each rank of a multi-GPU job.  The batch's
  * pinned host buffers are placed on the GPU's node regardless (FRX_NUMA=0 disables both).  The reference is a single

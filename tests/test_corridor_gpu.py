@@ -64,3 +64,23 @@ def test_path_to_trajectory_on_the_gpu():
         f = np.c_[f[:, :3] / np.linalg.norm(f[:, :3], axis=1, keepdims=True), f[:, 3:]]
         assert ((co[i, 5] - f[:, 3:]) * f[:, :3]).sum(1).max() < 0.3  # start point of the piece, up to the soft penalty's slack
     b.close()
+
+
+def test_batched_walks_on_the_device_match_the_host_walk():
+    """frx_cloud_generate_batch: the corridors of several candidate paths grown in lock-step (one batched device step per walk
+    step) are the polytopes the host walk builds for each path alone (faces as sets per polytope: see the near-tie note above)."""
+    rng = np.random.default_rng(31)
+    centres = synth.corridor_centres(rng, 14)
+    obs = synth.obstacle_cloud(31, centres, 50000)
+    base = synth.sample_path(centres)
+    paths = [base, base[: len(base) // 2], base[len(base) // 3:], base[::2]]
+    cloud = api.Cloud(obs)
+    got = cloud.generate_batch(paths, BBOX, 3.0)
+    for path, (off, faces) in zip(paths, got):
+        off_h, faces_h = api.corridor_generate(obs, path, BBOX, 3.0)
+        assert np.array_equal(off, off_h)
+        for k in range(len(off) - 1):
+            a, b = faces[off[k]:off[k + 1]], faces_h[off[k]:off[k + 1]]
+            key = lambda m: np.lexsort((m[:, 5], m[:, 4], m[:, 3], m[:, 2]))
+            assert np.abs(a[key(a)] - b[key(b)]).max() <= 1e-12
+    cloud.close()
