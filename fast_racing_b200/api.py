@@ -145,6 +145,7 @@ def load_library():
         "frx_batch_stream": (vp, [vp]),
         "frx_batch_host_buffers": (ci, [vp, P(P(cd)), P(P(cd)), P(P(cd))]),
         "frx_batch_set_reference_order": (ci, [vp, ci]),
+        "frx_batch_set_solver_slots": (ci, [vp, ci]),
         "frx_eval": (cd, [vp, P(cd), P(cd), ci]),
         "frx_batch_optimize": (ci, [vp, cd, P(cd), P(cd), P(cd), P(cd), P(ci), P(ci), P(ci), P(cd)]),
         "frx_batch_argmin": (ci, [vp, P(ci), P(cd)]),
@@ -183,7 +184,7 @@ EXPORTED_SYMBOLS = [
     "frx_batch_piece_offsets", "frx_batch_tables", "frx_batch_vpolys", "frx_batch_initial_guess", "frx_batch_eval",
     "frx_batch_eval_device", "frx_batch_eval_launches", "frx_batch_stream", "frx_batch_host_buffers", "frx_batch_set_reference_order", "frx_eval", "frx_batch_optimize", "frx_batch_argmin",
     "frx_batch_last_ms", "frx_strerror", "frx_version", "frx_device_numa_node", "frx_bind_thread_to_device",
-    "frx_batch_argmin_allgather", "frx_corridor_dilate", "frx_corridor_generate", "frx_cloud_create", "frx_cloud_destroy",
+    "frx_batch_argmin_allgather", "frx_batch_set_solver_slots", "frx_corridor_dilate", "frx_corridor_generate", "frx_cloud_create", "frx_cloud_destroy",
     "frx_cloud_dilate_batch", "frx_cloud_generate_batch",
 ]
 
@@ -397,6 +398,10 @@ class Batch:
     def set_reference_order(self, on=True):
         """Reference-order mode: bit-identical to the reference CPU code, slow (validation / reproducibility)."""
         _check(self.lib.frx_batch_set_reference_order(self.h, 1 if on else 0), "set_reference_order")
+
+    def set_solver_slots(self, slots):
+        """Queue-fed solver slots (0 = one per trajectory): see frx_batch_set_solver_slots."""
+        _check(self.lib.frx_batch_set_solver_slots(self.h, int(slots)), "set_solver_slots")
 
     def host_buffers(self):
         """numpy views of the batch's pinned host buffers (x, cost, grad): eval_pinned() transfers straight from/to them."""

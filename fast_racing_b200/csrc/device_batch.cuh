@@ -42,6 +42,11 @@ struct BatchView {
     const DevParams* par;   // B
     const double* headtail; // 18*B : head PVA (col-major 3x3) then tail PVA
     const int* active;      // B, or nullptr: trajectories with active[b]==0 are skipped (batched solver mask)
+    // Slot mode of the batched solver (solver.cuh "queue-fed slots"): when slot_list != nullptr the evaluation kernels run over
+    // n_slots entries, entry s naming the trajectory currently solved in slot s (or -1: empty slot)
+    const int* slot_list;
+    int n_slots;
+    int max_pieces;         // max pieces of any trajectory (grid of the penalty kernel in slot mode)
     // per coarse polytope
     const int* intervals;   // sum coarseN
     // per piece (global piece index)

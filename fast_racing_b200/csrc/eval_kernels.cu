@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "device_batch.cuh"
+#include "bulk_copy.cuh"
 
 #ifdef FRX_EXACT
 #define FRX_IMPL frx_exact  // reference-order build: -DFRX_EXACT --fmad=false (see build.py)
@@ -124,44 +125,6 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// ---- 1-D bulk copies global -> shared memory through the TMA unit, completion on an mbarrier (sm_90+/sm_100a) ----
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy before the first copy
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-// bytes: a multiple of 16; both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes),
-                 "r"(a)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(a),
-        "r"(parity)
-        : "memory");
-}
-
-// One bulk (TMA-unit) prefetch of a whole byte range into L2: the 16-byte aligned interior of [p, p + bytes).
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
-    const unsigned long long a = ((unsigned long long)p + 15ull) & ~15ull, e = ((unsigned long long)p + bytes) & ~15ull;
-    if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
-}
-
 #ifdef FRX_EXACT  // reference-order build only: the banded system in the reference's own elimination order
 // K1 ---------------------------------------------------------------------------------------------
 // One trajectory per CTA of two warps.
@@ -244,8 +207,9 @@ __device__ __forceinline__ void retire_rows(const double* ring, double* lug, dou
 // smem: ring[RING][16] | scratch[32] | ust[N][UST] (head aliased by Tc[coarseN] during the prologue, tail by the T/q staging)
 __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
-    const int b = bv.sub_traj0 + blockIdx.x;
-    if (bv.active && !bv.active[b]) return;
+    const int b = bv.slot_list ? bv.slot_list[blockIdx.x] : bv.sub_traj0 + blockIdx.x;
+    if (b < 0) return;  // empty solver slot
+    if (!bv.slot_list && bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
@@ -489,8 +453,19 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 __global__ void __launch_bounds__(PEN_THREADS, FRX_PEN_MINBLOCKS) penalty_kernel(BatchView bv, PenaltyLaunch pl) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
-    const int gp_base = bv.sub_piece0 + blockIdx.x * pl.ppc;
-    const int npieces = min(pl.ppc, bv.sub_piece1 - gp_base);
+    int gp_base, npieces;
+    if (bv.slot_list) {  // slot mode: CTA = (solver slot, group of ppc pieces of that slot's trajectory)
+        const int groups = (bv.max_pieces + pl.ppc - 1) / pl.ppc;
+        const int slot = blockIdx.x / groups, grp = blockIdx.x - slot * groups;
+        const int b = bv.slot_list[slot];
+        if (b < 0) return;
+        gp_base = bv.piece_off[b] + grp * pl.ppc;
+        npieces = min(pl.ppc, bv.piece_off[b + 1] - gp_base);
+        if (npieces <= 0) return;
+    } else {
+        gp_base = bv.sub_piece0 + blockIdx.x * pl.ppc;
+        npieces = min(pl.ppc, bv.sub_piece1 - gp_base);
+    }
     double* cf = sm;
     double* fc = cf + (size_t)pl.ppc * CF;
     double* part = fc + (size_t)pl.ppc * 6 * bv.max_faces;
@@ -808,9 +783,15 @@ __device__ __forceinline__ void ex_normalizeFDF(const double* x, double* xNor, d
 }
 
 __global__ void __launch_bounds__(32) penalty_exact_kernel(BatchView bv) {
-    const int b = bv.sub_traj0 + blockIdx.x * 32 + threadIdx.x;
-    if (b >= bv.sub_traj1) return;
-    if (bv.active && !bv.active[b]) return;
+    int b = bv.sub_traj0 + blockIdx.x * 32 + threadIdx.x;
+    if (bv.slot_list) {
+        if (b >= bv.n_slots) return;
+        b = bv.slot_list[b];
+        if (b < 0) return;
+    } else {
+        if (b >= bv.sub_traj1) return;
+        if (bv.active && !bv.active[b]) return;
+    }
     const int p0 = bv.piece_off[b];
     const int N = bv.piece_off[b + 1] - p0;
     const DevParams P = bv.par[b];
@@ -1036,8 +1017,9 @@ __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
     extern __shared__ double sm[];
-    const int b = bv.sub_traj0 + blockIdx.x;
-    if (bv.active && !bv.active[b]) return;
+    const int b = bv.slot_list ? bv.slot_list[blockIdx.x] : bv.sub_traj0 + blockIdx.x;
+    if (b < 0) return;  // empty solver slot
+    if (!bv.slot_list && bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
@@ -1400,8 +1382,9 @@ __host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
 // smem (doubles): Tc[coarseN+1] | Ts[M] | iT[M] | P[3(M+1)] | Y[6(M+1)] | nD[3M] | nL[4M] | nR[6M] | nG[4M] | wpi[3M ints]
 __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const double* __restrict__ xin) {
     extern __shared__ double sm[];
-    const int b = bv.sub_traj0 + blockIdx.x;
-    if (bv.active && !bv.active[b]) return;
+    const int b = bv.slot_list ? bv.slot_list[blockIdx.x] : bv.sub_traj0 + blockIdx.x;
+    if (b < 0) return;  // empty solver slot
+    if (!bv.slot_list && bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
@@ -1642,8 +1625,9 @@ __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
                           double* __restrict__ grad_out) {
     extern __shared__ __align__(16) double sm[];
-    const int b = bv.sub_traj0 + blockIdx.x;
-    if (bv.active && !bv.active[b]) return;
+    const int b = bv.slot_list ? bv.slot_list[blockIdx.x] : bv.sub_traj0 + blockIdx.x;
+    if (b < 0) return;  // empty solver slot
+    if (!bv.slot_list && bv.active && !bv.active[b]) return;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int p0 = bv.piece_off[b];
@@ -2024,9 +2008,10 @@ cudaError_t configure_kernels(size_t fwd_smem, size_t bwd_smem, size_t pen_smem)
 
 static void launch_penalty(const BatchView& bv, const PenaltyLaunch& pl, cudaStream_t st) {
 #ifdef FRX_EXACT
-    penalty_exact_kernel<<<(bv.sub_traj1 - bv.sub_traj0 + 31) / 32, 32, 0, st>>>(bv);
+    const int nt = bv.slot_list ? bv.n_slots : bv.sub_traj1 - bv.sub_traj0;
+    penalty_exact_kernel<<<(nt + 31) / 32, 32, 0, st>>>(bv);
 #else
-    const int grid = (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
+    const int grid = bv.slot_list ? bv.n_slots * ((bv.max_pieces + pl.ppc - 1) / pl.ppc) : (bv.sub_piece1 - bv.sub_piece0 + pl.ppc - 1) / pl.ppc;
     penalty_kernel<<<grid, pl.threads, pl.smem, st>>>(bv, pl);
 #endif
 }
@@ -2040,12 +2025,13 @@ cudaError_t launch_eval_pipelined(const BatchView& bv0, const PenaltyLaunch& pl,
                                   cudaEvent_t ev_fork, cudaEvent_t ev_k1, cudaEvent_t ev_join, const int* piece_off_host,
                                   int nsub) {
     const int B = bv0.B;
-    if (nsub < 2 || B < 2 * nsub || !aux) {
+    if (nsub < 2 || B < 2 * nsub || !aux || bv0.slot_list) {  // solver slots: always one launch over the slots
         BatchView bv = bv0;
         bv.sub_traj0 = 0, bv.sub_traj1 = B, bv.sub_piece0 = 0, bv.sub_piece1 = bv.total_pieces;
-        minco_forward_kernel<<<B, 64, fwd_smem, st>>>(bv, x_dev);
+        const int grid = bv.slot_list ? bv.n_slots : B;  // slot mode: one CTA per solver slot
+        minco_forward_kernel<<<grid, 64, fwd_smem, st>>>(bv, x_dev);
         launch_penalty(bv, pl, st);
-        minco_backward_kernel<<<B, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
+        minco_backward_kernel<<<grid, 64, bwd_smem, st>>>(bv, x_dev, cost_dev, grad_dev);
         return cudaGetLastError();
     }
     cudaEventRecord(ev_fork, st);

@@ -75,6 +75,7 @@ struct frx_batch {
     cudaStream_t stream = nullptr, aux = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_k1 = nullptr, ev_join = nullptr;
     int e2e_chunks = 2;  // chunks of the host-buffer path: copies of one chunk overlap the kernels of the other (FRX_E2E_CHUNKS)
+    int solver_slots = 0;  // frx_batch_set_solver_slots: 0 = one slot per trajectory
     int nsub = 1;  // sub-batches of the pipelined evaluation (FRX_EVAL_SUBBATCHES); measured on B200: K2 fills the register
                    // file (8 CTAs x 64 thr x 128 regs), so K1/K3 cannot co-reside and pipelining only adds tails -> default off
     cudaError_t eval_on(const double* x, double* cost, double* grad, cudaStream_t st) {
@@ -587,6 +588,7 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
     BatchView& bv = b->bv;
     bv.B = B, bv.total_pieces = TP, bv.total_x = b->x_off[B];
     bv.max_faces = max_faces, bv.max_samples = max_samples;
+    bv.slot_list = nullptr, bv.n_slots = 0, bv.max_pieces = b->max_M;
     b->fwd_smem = frx_fast::forward_smem_bytes(b->max_M, b->max_coarse);
     b->bwd_smem = frx_fast::backward_smem_bytes(b->max_M, b->max_coarse);
     b->fwd_smem_x = frx_exact::forward_smem_bytes(b->max_M, b->max_coarse);
@@ -924,6 +926,12 @@ int frx_batch_argmin_allgather(frx_batch* b, void* nccl_comm, int n_ranks, long 
     return FRX_OK;
 }
 
+int frx_batch_set_solver_slots(frx_batch* b, int slots) {
+    if (!b || slots < 0) return FRX_ERR_INVALID_ARG;
+    b->solver_slots = slots;
+    return FRX_OK;
+}
+
 int frx_batch_set_reference_order(frx_batch* b, int on) {
     if (!b) return FRX_ERR_INVALID_ARG;
     b->exact = on != 0;
@@ -1019,6 +1027,8 @@ int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* 
     io.x0_host = x0.data();
     io.rel_tol = rel_tol;
     io.stream = b->stream;
+    io.slots = b->solver_slots;
+    if (const char* e = getenv("FRX_SOLVER_SLOTS")) io.slots = atoi(e);
     if (const char* e = getenv("FRX_SOLVER_MAX_TICKS")) io.max_ticks = atoi(e) > 0 ? atoi(e) : io.max_ticks;  // tests: truncated runs
     auto eval = [b](const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st) {
         return b->eval_on(x_dev, cost_dev, grad_dev, st);

@@ -1,5 +1,6 @@
 // Batched device-side L-BFGS — see solver.cuh for the design.
 #include "solver.cuh"
+#include "bulk_copy.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -206,21 +207,164 @@ __device__ __forceinline__ void blocked_recursion(const double* __restrict__ Mx,
     }
 }
 
-__device__ void direction_vector_free(const SolverView& sv, int b, int n, int m, int end, int bound,
+// The history of one trajectory streamed through shared memory by the TMA unit, through a ring of UPD_NST stages of `ch`
+// doubles, so that the next UPD_NST - 1 chunks are in flight while the CTA works on one.  (The plain-load passes below run at
+// about one DRAM latency per unrolled trip: 1.8 TB/s over 256 CTAs, 3.1 TB/s over 1024; scripts/micro/stream_bench.cu is the
+// stand-alone measurement behind the ring.)  Rows are padded to an even length ld, so any row segment that starts at an even
+// column and has an even length is a legal bulk copy (16-byte aligned, multiple of 16 bytes).
+//   pass 1  chunk = tile of 8 rows x W columns of S or Y (8 copies, one per row segment, row stride W + 4 doubles in the
+//           stage: conflict-free fragment loads), order: row block, array, column tile;
+//   pass 2  chunk = R2 whole rows of S or Y (one copy), order: the reverse of pass 1's rows (what was streamed last is
+//           what the L2 still holds).
+#define UPD_NST_MAX 8  // ring stages: sv.upd_nst <= UPD_NST_MAX
+#define UPD_PART (2 * 8 * 8 * 3)  // doubles: the eight per-warp partial 8 x 3 tiles of two row blocks
+#define UPD_COLS 8                // columns per thread in pass 2: n <= UPD_COLS * UPD_THREADS
+struct HistStream {
+    double* ring;              // nst * ch doubles
+    unsigned long long* full;  // nst mbarriers
+    const double* S;
+    const double* Y;
+    int n, ld, m, ch, nst;
+    int W, CT;  // pass 1: tile width (multiple of 32, or ld when one tile covers a row), column tiles per row
+    int R2;     // pass 2: rows per chunk
+};
+// pass 1, chunk q = (rb * 2 + arr) * CT + ct
+__device__ __forceinline__ void hist_issue_tile(const HistStream& hs, int seq, int q) {
+    const int ct = q % hs.CT, ga = q / hs.CT, arr = ga & 1, rb = ga >> 1;
+    const int c0 = ct * hs.W, wt = min(hs.W, hs.ld - c0);
+    const int stg = seq % hs.nst;
+    double* dst = hs.ring + (size_t)stg * hs.ch;
+    const double* src = (arr ? hs.Y : hs.S) + (size_t)(rb * 8) * hs.ld + c0;
+    mbar_expect_tx(hs.full + stg, 8u * (unsigned)wt * 8u);
+#pragma unroll
+    for (int r = 0; r < 8; r++) bulk_g2s(dst + (size_t)r * (hs.W + 4), src + (size_t)r * hs.ld, (unsigned)wt * 8u, hs.full + stg);
+}
+// pass 2, chunk q: array q & 1, rows [R2 (q >> 1), ...)
+__device__ __forceinline__ void hist_issue_rows(const HistStream& hs, int seq, int q) {
+    const int r0 = (q >> 1) * hs.R2, rows = min(hs.R2, hs.m - r0);
+    const unsigned bytes = (unsigned)(rows * hs.ld) * 8u;
+    const int stg = seq % hs.nst;
+    mbar_expect_tx(hs.full + stg, bytes);
+    bulk_g2s(hs.ring + (size_t)stg * hs.ch, ((q & 1) ? hs.Y : hs.S) + (size_t)r0 * hs.ld, bytes, hs.full + stg);
+}
+// D (8 x 8) += A (8 x 4, row-major fragment: lane holds A[lane / 4][lane % 4]) * B (4 x 8: lane holds B[lane % 4][lane / 4]);
+// lane holds D[lane / 4][2 (lane % 4) + {0, 1}].  fp64 tensor-core MMA (DMMA), fp64 accumulation.
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld, int m, int end, int bound,
                                       const double* __restrict__ g, double* __restrict__ d, const double* __restrict__ S,
-                                      const double* __restrict__ Y, double* ysv UPD_MARK_ARG) {
+                                      const double* __restrict__ Y, double* ysv, double* dyn UPD_MARK_ARG) {
     __shared__ double sg[128], yg[128], cb[128], ca[128], tv[128], al[128];
     __shared__ double sh_gamma;
+    __shared__ unsigned long long full_bar[UPD_NST_MAX];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double* SY = sv.SY + (size_t)b * m * m;
     double* SYT = sv.SYT + (size_t)b * m * m;
     double* YY = sv.YY + (size_t)b * m * m;
-    const double* sn = S + (size_t)end * n;
-    const double* yn = Y + (size_t)end * n;
+    const double* sn = S + (size_t)end * ld;
+    const double* yn = Y + (size_t)end * ld;
+    // streamed passes: a stage holds two rows (pass 2) and an 8 x 32 tile (pass 1) at least; history depth a multiple of 8;
+    // UPD_COLS columns per thread in pass 2 at most
+    HistStream hs;
+    hs.ring = dyn, hs.full = full_bar, hs.S = S, hs.Y = Y, hs.n = n, hs.ld = ld, hs.m = m, hs.ch = sv.upd_ch, hs.nst = sv.upd_nst;
+    const int NST = sv.upd_nst;
+    {
+        const int wmax = (sv.upd_ch / 8 - 4) & ~31;  // widest tile the stage holds, multiple of 32
+        hs.W = (ld <= wmax || wmax < 32) ? ld : wmax;
+        hs.CT = (ld + hs.W - 1) / hs.W;
+        hs.R2 = max(1, min(m, sv.upd_ch / ld));
+    }
+    const bool streamed = dyn != nullptr && ld <= sv.upd_ch && 8 * (hs.W + 4) <= sv.upd_ch && (m & 7) == 0 && n <= UPD_COLS * UPD_THREADS;
+    const int Q1 = 2 * ((bound + 7) >> 3) * hs.CT;       // chunks of pass 1
+    const int Q2 = 2 * ((bound + hs.R2 - 1) / hs.R2);    // chunks of pass 2
+    const int nv = (n + 1) & ~1;
+    double* part = dyn + (size_t)NST * sv.upd_ch;  // [2][8 warps][8 rows][3]
+    double* vec = part + UPD_PART;                      // y_new, s_new, g: the B operand of pass 1
+    if (streamed) {
+        if (tid == 0) {
+#pragma unroll
+            for (int i = 0; i < UPD_NST_MAX; i++)
+                if (i < NST) mbar_init(full_bar + i, 1);
+        }
+        for (int i = tid; i < n; i += UPD_THREADS) vec[i] = yn[i], vec[nv + i] = sn[i], vec[2 * nv + i] = g[i];
+        // rows `end` of S and Y were stored by this CTA a moment ago (generic proxy); the bulk copies below read them through
+        // the async proxy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+        if (tid == 0)
+            for (int q = 0; q < min(NST, Q1); q++) hist_issue_tile(hs, q, q);
+        // ---- pass 1 (streamed): P[row][j] = row . (y_new, s_new, g)[j] for every row of S and Y, on the fp64 tensor cores:
+        // A = 8 rows x 4 columns of the tile, B = 4 entries of the three vectors (columns 3..7 of B are zero), so one DMMA
+        // retires 8 x 4 x 3 useful products for one shared-memory load per operand, and the sum over a row's columns happens
+        // in the accumulators instead of in shuffles.  The eight warps split a tile's columns; their accumulators run over
+        // the column tiles of a row block, and the eight partial 8 x 3 tiles are then added in warp order by the threads that
+        // store the Gram entries, one chunk later (so a chunk costs one CTA barrier).
+        const int gid = lane >> 2, TS = hs.W + 4;
+        const double* bsrc = vec + (size_t)min(gid, 2) * nv;
+        auto flush = [&](int ga) {  // partial tiles of (row block, array) group ga -> Gram entries
+            const int r0 = (ga >> 1) * 8, rows = min(8, bound - r0);
+            if (tid < 3 * rows) {
+                const int row = tid / 3, col = tid - 3 * row, l = r0 + row;
+                const double* pp = part + (size_t)(ga & 1) * (8 * 8 * 3) + row * 3 + col;
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) v += pp[w * 8 * 3];
+                if (!(ga & 1)) {  // s_l
+                    if (col == 0) SY[(size_t)l * m + end] = v, SYT[(size_t)end * m + l] = v;
+                    if (col == 2) sg[l] = v;
+                } else {  // y_l
+                    if (col == 0) YY[(size_t)l * m + end] = v, YY[(size_t)end * m + l] = v;
+                    if (col == 1 && l != end) SY[(size_t)end * m + l] = v, SYT[(size_t)l * m + end] = v;
+                    if (col == 2) yg[l] = v;
+                }
+            }
+        };
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: the DMMAs of a tile alternate between them
+        for (int q = 0; q < Q1; q++) {
+            const int stg = q % NST;
+            const int ct = q % hs.CT, ga = q / hs.CT;
+            mbar_wait(full_bar + stg, (q / NST) & 1);
+            if (ct == 0 && ga > 0) flush(ga - 1);
+            const int col0 = ct * hs.W, wt = min(hs.W, ld - col0);
+            const int rows = min(8, bound - (ga >> 1) * 8);
+            const int kper = ((((wt + 7) >> 3) + 7) >> 3) << 3, KS2 = kper >> 3;  // columns per warp: a multiple of 8
+            const int kb = warp * kper + (lane & 3);
+            const double* arow = dyn + (size_t)stg * hs.ch + (size_t)gid * TS;
+            const double* brow = bsrc + col0;
+            const bool rok = gid < rows, bok = gid < 3;
+            const int klim = min(wt, n - col0);  // columns of this tile that exist
+#pragma unroll 2
+            for (int ks = 0; ks < KS2; ks++) {
+                const int ka = kb + 8 * ks, kc = ka + 4;
+                const double av = (rok && ka < klim) ? arow[ka] : 0.0;
+                const double aw = (rok && kc < klim) ? arow[kc] : 0.0;
+                const double bv = (bok && ka < klim) ? brow[ka] : 0.0;
+                const double bw = (bok && kc < klim) ? brow[kc] : 0.0;
+                dmma_884(c0, c1, av, bv);
+                dmma_884(e0, e1, aw, bw);
+            }
+            if (ct == hs.CT - 1) {
+                double* pw = part + (size_t)(ga & 1) * (8 * 8 * 3) + warp * (8 * 3);
+                if (rok) {
+                    if ((lane & 3) == 0) pw[gid * 3] = c0 + e0, pw[gid * 3 + 1] = c1 + e1;
+                    if ((lane & 3) == 1) pw[gid * 3 + 2] = c0 + e0;
+                }
+                c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+            }
+            __syncthreads();  // every thread is done with this stage (refill it); the partial tiles of a finished group are complete
+            if (tid == 0 && q + NST < Q1) hist_issue_tile(hs, q + NST, q + NST);
+        }
+        flush(Q1 / hs.CT - 1);
+        // the first chunks of pass 2 are requested now and arrive under the two recursions
+        if (tid == 0)
+            for (int j = 0; j < min(NST, Q2); j++) hist_issue_rows(hs, Q1 + j, Q2 - 1 - j);
+    } else
     // ---- pass 1 ----
     for (int l = warp; l < bound; l += UPD_THREADS / 32) {
-        const double* sl = S + (size_t)l * n;
-        const double* yl = Y + (size_t)l * n;
+        const double* sl = S + (size_t)l * ld;
+        const double* yl = Y + (size_t)l * ld;
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
         // 8 elements per lane per trip, all loads issued before use (HBM-latency bound otherwise)
         for (int i0 = lane; i0 < n; i0 += 256) {
@@ -313,6 +457,30 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
     blocked_recursion<2>(SYT, m, bound, tacc, rys, al, ca, dblk, cbk, slot);
     UPD_MARK(7);
     // ---- pass 2: d = dg*g + sum_l ca_l s_l + cb_l y_l ----
+    if (streamed) {
+        double acc[UPD_COLS];
+#pragma unroll
+        for (int e = 0; e < UPD_COLS; e++) acc[e] = (tid + e * UPD_THREADS < n) ? dg * vec[2 * nv + tid + e * UPD_THREADS] : 0.0;
+        for (int j = 0; j < Q2; j++) {
+            const int seq = Q1 + j, q = Q2 - 1 - j, stg = seq % NST;
+            mbar_wait(full_bar + stg, (seq / NST) & 1);
+            const int r0 = (q >> 1) * hs.R2, rows = min(hs.R2, bound - r0);
+            const double* chunk = dyn + (size_t)stg * hs.ch;
+            const double* cf = ((q & 1) ? cb : ca) + r0;
+#pragma unroll 2
+            for (int r = 0; r < rows; r++) {
+                const double co = cf[r];
+#pragma unroll
+                for (int e = 0; e < UPD_COLS; e++)
+                    if (tid + e * UPD_THREADS < n) acc[e] += co * chunk[(size_t)r * ld + tid + e * UPD_THREADS];
+            }
+            __syncthreads();
+            if (tid == 0 && j + NST < Q2) hist_issue_rows(hs, seq + NST, q - NST);
+        }
+#pragma unroll
+        for (int e = 0; e < UPD_COLS; e++)
+            if (tid + e * UPD_THREADS < n) d[tid + e * UPD_THREADS] = acc[e];
+    } else
     for (int base = 0; base < n; base += UPD_THREADS * 4) {
         double acc[4];
         int idx[4];
@@ -325,8 +493,8 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
 #pragma unroll 8
         for (int l = bound - 1; l >= 0; l--) {
             const double a = ca[l], bb = cb[l];
-            const double* sl = S + (size_t)l * n;
-            const double* yl = Y + (size_t)l * n;
+            const double* sl = S + (size_t)l * ld;
+            const double* yl = Y + (size_t)l * ld;
 #pragma unroll
             for (int e = 0; e < 4; e++)
                 if (idx[e] < n) acc[e] += a * sl[idx[e]] + bb * yl[idx[e]];
@@ -340,14 +508,14 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int m,
 }
 
 // The sequential two-loop recursion in the reference's order (lbfgs.hpp:1359-1411) on dv, which holds -g on entry.
-__device__ void direction_two_loop(double* dv, int n, int m, int end1, int bound, const double* S, const double* Y, const double* ysv,
+__device__ void direction_two_loop(double* dv, int n, int ld, int m, int end1, int bound, const double* S, const double* Y, const double* ysv,
                                    double* alv, double ys, double yy, double* red) {
     const int tid = threadIdx.x;
     int j = end1;
     for (int it = 0; it < bound; it++) {
         j = (j + m - 1) % m;
-        const double* sj = S + (size_t)j * n;
-        const double* yj = Y + (size_t)j * n;
+        const double* sj = S + (size_t)j * ld;
+        const double* yj = Y + (size_t)j * ld;
         const double a = block_dot(sj, dv, n, red) / ysv[j];
         if (tid == 0) alv[j] = a;
         const double c = -a;
@@ -359,8 +527,8 @@ __device__ void direction_two_loop(double* dv, int n, int m, int end1, int bound
     }
     __syncthreads();  // alv[] written by thread 0 above
     for (int it = 0; it < bound; it++) {
-        const double* sj = S + (size_t)j * n;
-        const double* yj = Y + (size_t)j * n;
+        const double* sj = S + (size_t)j * ld;
+        const double* yj = Y + (size_t)j * ld;
         const double beta = block_dot(yj, dv, n, red) / ysv[j];
         const double c = alv[j] - beta;
         for (int i = tid; i < n; i += UPD_THREADS) dv[i] += c * sj[i];
@@ -372,12 +540,14 @@ __device__ void direction_two_loop(double* dv, int n, int m, int end1, int bound
 enum : int { ACT_TRIAL = 0, ACT_FINISH = 1, ACT_NEXT_ITER = 2 };
 
 __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv) {
-    const int b = blockIdx.x;
+    const int b = sv.slot_list[blockIdx.x];
+    if (b < 0) return;  // empty slot
     TrajSolve* st = sv.st + b;
     if (st->phase == PH_DONE) return;
     __shared__ double red[16];
     __shared__ int sh_act;
     __shared__ double sh_step;
+    extern __shared__ __align__(128) double upd_dyn[];  // ring + vectors of the streamed direction update (0 bytes: plain loads)
     const int tid = threadIdx.x;
     const int n = sv.x_off[b + 1] - sv.x_off[b];
     const size_t xo = (size_t)sv.x_off[b];
@@ -387,8 +557,10 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
     double* gp = sv.gp + xo;
     double* d = sv.d + xo;
     const int m = sv.cfg.mem_size;
-    double* S = sv.S + (size_t)m * xo;
-    double* Y = sv.Y + (size_t)m * xo;
+    // history rows are padded to an even number of doubles (16-byte aligned rows: bulk copies of row segments)
+    const int ld = (n + 1) & ~1;
+    double* S = sv.S + (size_t)m * (xo + b);
+    double* Y = sv.Y + (size_t)m * (xo + b);
     double* ysv = sv.ys + (size_t)m * b;
     double* alv = sv.alpha + (size_t)m * b;
     const LbfgsConfig& P = sv.cfg;
@@ -492,8 +664,8 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
             if (sh_act == ACT_NEXT_ITER) {
                 const int end = st->end;
                 const int k = st->k;
-                double* se = S + (size_t)end * n;
-                double* ye = Y + (size_t)end * n;
+                double* se = S + (size_t)end * ld;
+                double* ye = Y + (size_t)end * ld;
                 for (int i = tid; i < n; i += UPD_THREADS) {
                     se[i] = x[i] - xp[i];
                     ye[i] = g[i] - gp[i];
@@ -513,12 +685,12 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
                 // measurement only: the direction update streams the history twice, (4 bound + 4) n doubles
                 if (sv.count_bytes && tid == 0) atomicAdd(sv.hist_bytes, 8ull * (4ull * bound + 4ull) * (unsigned long long)n);
                 if (sv.vector_free) {
-                    direction_vector_free(sv, b, n, m, end, bound, g, d, S, Y, ysv UPD_MARK_PASS);
+                    direction_vector_free(sv, b, n, ld, m, end, bound, g, d, S, Y, ysv, sv.upd_smem ? upd_dyn : nullptr UPD_MARK_PASS);
                     if (sv.check_dir) {  // self-check (FRX_LBFGS_CHECK=1): the two-loop recursion on a scratch vector
                         double* dc = sv.dchk + xo;
                         for (int i = tid; i < n; i += UPD_THREADS) dc[i] = -g[i];
                         __syncthreads();
-                        direction_two_loop(dc, n, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
+                        direction_two_loop(dc, n, ld, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
                         double emax = 0.0, dmax = 0.0;
                         for (int i = tid; i < n; i += UPD_THREADS) emax = fmax(emax, fabs(d[i] - dc[i])), dmax = fmax(dmax, fabs(dc[i]));
                         __shared__ double chk[2][UPD_THREADS / 32];
@@ -536,7 +708,7 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
                     if (tid == 0) st->step = 1.0;
                     start_iter = true;
                 } else {
-                direction_two_loop(d, n, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
+                direction_two_loop(d, n, ld, m, end1, bound, S, Y, ysv, alv, ys, yy, red);
                 if (tid == 0) st->step = 1.0;
                 start_iter = true;
                 }
@@ -585,6 +757,13 @@ __global__ void __launch_bounds__(UPD_THREADS) lbfgs_update_kernel(SolverView sv
             st->phase = PH_DONE;
             sv.active[b] = 0;
             atomicSub(sv.n_active, 1);
+            // hand the slot to the next pending trajectory (its state is PH_INIT, its x the start point): evaluated next tick
+            const int nx = atomicAdd(sv.next_pending, 1);
+            if (nx < sv.B) {
+                sv.active[nx] = 1;
+                sv.slot_list[blockIdx.x] = nx;
+            } else
+                sv.slot_list[blockIdx.x] = -1;
         }
     }
     UPD_MARK(10);
@@ -682,15 +861,51 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
     }
     const size_t nx = (size_t)bv.total_x;
     const size_t m = (size_t)sv.cfg.mem_size;
+    sv.upd_smem = 0, sv.upd_ch = 0, sv.upd_nst = 0;
+#ifndef FRX_EXACT
+    {
+        // Streamed direction update: ring of UPD_NST stages + partial tiles + (y_new, s_new, g).  Two CTAs per SM while the
+        // largest trajectory allows it (one streams while the other runs its recursions), one CTA per SM with a deeper ring
+        // beyond; plain loads when even that does not hold two rows per stage.  FRX_LBFGS_STREAM=0 forces plain loads.
+        int max_n = 0;
+        for (size_t i = 0; i + 1 < x_off.size(); i++) max_n = std::max(max_n, x_off[i + 1] - x_off[i]);
+        const char* e = getenv("FRX_LBFGS_STREAM");
+        if (sv.vector_free && !(e && e[0] == '0') && max_n <= UPD_COLS * UPD_THREADS) {
+            // Few trajectories (at most two per SM anyway): one CTA per SM with a deep ring streams fastest.  Many: two CTAs per
+            // SM, so that one streams while the other runs its recursions.  (profiles/r02_update_kernel.txt has the sweep.)
+            const int ldm = (max_n + 1) & ~1, fixed = UPD_PART + 3 * ldm;
+            struct Cfg { int budget_kb, nst; };
+            const bool few = bv.B <= 2 * 148;
+            Cfg cfgs[3] = {few ? Cfg{200, 4} : Cfg{96, 3}, Cfg{200, 4}, Cfg{200, 2}};
+            if (const char* eb = getenv("FRX_UPD_BUDGET_KB")) cfgs[0].budget_kb = atoi(eb);  // experiments
+            if (const char* en = getenv("FRX_UPD_NST")) cfgs[0].nst = std::max(2, std::min(UPD_NST_MAX, atoi(en)));
+            for (const Cfg& c : cfgs) {
+                const int ch = ((c.budget_kb * 1024 / 8 - fixed) / c.nst) & ~1;
+                if (ch >= ldm && ch >= 8 * (32 + 4)) {
+                    sv.upd_ch = std::min(ch, std::max(8 * (((ldm + 31) & ~31) + 4), 2 * ldm));  // no more than one row block x whole rows
+                    sv.upd_nst = c.nst;
+                    sv.upd_smem = (int)(sizeof(double) * ((size_t)c.nst * sv.upd_ch + fixed));
+                    break;
+                }
+            }
+            if (sv.upd_smem &&
+                cudaFuncSetAttribute(lbfgs_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sv.upd_smem) != cudaSuccess) {
+                delete s;
+                return FRX_ERR_CUDA;
+            }
+        }
+    }
+#endif
     int* xo = nullptr;
     bool ok = dalloc(s, x_off.size(), &xo) == cudaSuccess &&
               cudaMemcpy(xo, x_off.data(), sizeof(int) * x_off.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     sv.x_off = xo;
     ok = ok && dalloc(s, (size_t)bv.B, &sv.st) == cudaSuccess && dalloc(s, (size_t)bv.B, &sv.active) == cudaSuccess &&
-         dalloc(s, 1, &sv.n_active) == cudaSuccess && dalloc(s, nx, &sv.x) == cudaSuccess &&
+         dalloc(s, 1, &sv.n_active) == cudaSuccess && dalloc(s, (size_t)bv.B, &sv.slot_list) == cudaSuccess &&
+         dalloc(s, 1, &sv.next_pending) == cudaSuccess && dalloc(s, nx, &sv.x) == cudaSuccess &&
          dalloc(s, nx, &sv.g) == cudaSuccess && dalloc(s, (size_t)bv.B, &sv.cost) == cudaSuccess &&
          dalloc(s, nx, &sv.xp) == cudaSuccess && dalloc(s, nx, &sv.gp) == cudaSuccess && dalloc(s, nx, &sv.d) == cudaSuccess &&
-         dalloc(s, m * nx, &sv.S) == cudaSuccess && dalloc(s, m * nx, &sv.Y) == cudaSuccess &&
+         dalloc(s, m * (nx + bv.B), &sv.S) == cudaSuccess && dalloc(s, m * (nx + bv.B), &sv.Y) == cudaSuccess &&
          dalloc(s, m * bv.B, &sv.ys) == cudaSuccess && dalloc(s, m * bv.B, &sv.alpha) == cudaSuccess &&
          dalloc(s, m * m * bv.B, &sv.SY) == cudaSuccess && dalloc(s, m * m * bv.B, &sv.SYT) == cudaSuccess &&
          dalloc(s, m * m * bv.B, &sv.YY) == cudaSuccess &&
@@ -735,7 +950,7 @@ int solver_run(SolverState* s, BatchView& bv, const SolverIO& io, const EvalFn& 
     solver_bind_active(bv, s, true);
     struct Unbind {  // bv.active must be nullptr again on EVERY exit: a stale mask would make later evaluations skip trajectories
         BatchView& bv;
-        ~Unbind() { bv.active = nullptr; }
+        ~Unbind() { bv.active = nullptr, bv.slot_list = nullptr, bv.n_slots = 0; }
     } unbind{bv};
     int ticks = 0, n_active = bv.B;
     // Measurement: the first update launch of every poll group is bracketed by events and counts the history bytes it
@@ -829,19 +1044,25 @@ int solver_update_stats(SolverState* s, double* ms, double* bytes, int* samples)
     return FRX_OK;
 }
 const double* solver_final_cost_dev(SolverState* s) { return s->fx_dev; }
-void solver_bind_active(BatchView& bv, SolverState* s, bool on) { bv.active = on ? s->sv.active : nullptr; }
+void solver_bind_active(BatchView& bv, SolverState* s, bool on) {
+    bv.active = on ? s->sv.active : nullptr;
+    bv.slot_list = on ? s->sv.slot_list : nullptr;
+    bv.n_slots = on ? s->sv.n_slots : 0;
+}
 
-__global__ void init_active_kernel(int* active, int* n_active, int B) {
+__global__ void init_active_kernel(int* active, int* n_active, int* slot_list, int* next_pending, int B, int n_slots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) active[i] = 1;
-    if (i == 0) *n_active = B;
+    if (i < B) active[i] = i < n_slots;  // the first n_slots trajectories start, the others wait for a free slot
+    if (i < n_slots) slot_list[i] = i;
+    if (i == 0) *n_active = B, *next_pending = n_slots;
 }
 
 int solver_reset(SolverState* s, const SolverIO& io) {
     SolverView& sv = s->sv;
     sv.cfg.delta = io.rel_tol;
     if (cudaMemsetAsync(sv.st, 0, sizeof(TrajSolve) * sv.B, io.stream) != cudaSuccess) return FRX_ERR_CUDA;
-    init_active_kernel<<<(sv.B + 255) / 256, 256, 0, io.stream>>>(sv.active, sv.n_active, sv.B);
+    sv.n_slots = (io.slots > 0 && io.slots < sv.B) ? io.slots : sv.B;
+    init_active_kernel<<<(sv.B + 255) / 256, 256, 0, io.stream>>>(sv.active, sv.n_active, sv.slot_list, sv.next_pending, sv.B, sv.n_slots);
     if (cudaMemcpyAsync(sv.x, io.x0_host, sizeof(double) * s->total_x, cudaMemcpyHostToDevice, io.stream) != cudaSuccess)
         return FRX_ERR_CUDA;
     if (cudaStreamSynchronize(io.stream) != cudaSuccess) return FRX_ERR_CUDA;  // x0_host may be pageable
@@ -849,7 +1070,7 @@ int solver_reset(SolverState* s, const SolverIO& io) {
 }
 
 cudaError_t solver_launch_update(SolverState* s, cudaStream_t st) {
-    lbfgs_update_kernel<<<s->sv.B, UPD_THREADS, 0, st>>>(s->sv);
+    lbfgs_update_kernel<<<s->sv.n_slots, UPD_THREADS, (size_t)s->sv.upd_smem, st>>>(s->sv);
     return cudaGetLastError();
 }
 

@@ -35,7 +35,17 @@ struct SolverView {
     const int* x_off;   // B+1
     TrajSolve* st;      // B
     int* active;        // B: 1 while the trajectory still wants evaluations (read by the eval kernels)
-    int* n_active;      // 1
+    int* n_active;      // 1: trajectories not finished yet (of all B)
+    // Queue-fed slots: the kernels of a tick run over n_slots entries; slot_list[s] = trajectory being solved in slot s (-1:
+    // empty).  A trajectory that finishes hands its slot to the next pending one (next_pending), so a tick costs what the
+    // slots cost, not what the whole batch costs, and stragglers of an early wave overlap the bulk of a later one.
+    // n_slots == B: every trajectory has its own slot from the start (no queue).
+    int* slot_list;     // n_slots
+    int* next_pending;  // 1
+    int n_slots;
+    int upd_nst;        // ring stages of the streamed history passes
+    int upd_ch;         // doubles per ring stage of the streamed history passes
+    int upd_smem;       // dynamic shared memory of the update kernel (streamed history passes), 0: plain loads
     double *x, *g, *cost;          // current trial point / gradient / objective (packed)
     double *xp, *gp, *d;           // previous iterate, its gradient, search direction
     double *S, *Y;                 // history: trajectory b, slot j at mem_size*x_off[b] + j*n_b
@@ -54,6 +64,7 @@ struct SolverIO {
     double rel_tol = 1e-5;
     cudaStream_t stream = nullptr;
     int max_ticks = 400000;  // safety net only; the reference has no iteration limit (max_iterations = 0)
+    int slots = 0;           // solver slots (0 or >= B: one per trajectory)
     int poll_every = 8;
 };
 

@@ -130,6 +130,12 @@ int frx_batch_optimize(frx_batch *b, double rel_tol, double *durations, double *
                        double *final_cost, int *lbfgs_status, int *iterations, int *evaluations,
                        double *x_final);
 
+/* Queue-fed solver slots: with 0 < slots < count, frx_batch_optimize keeps `slots` trajectories in flight; a trajectory that
+ * finishes hands its slot to the next one of the batch, so a solver tick costs what the slots cost and the slowest
+ * trajectories of an early wave overlap the bulk of a later one.  Results per trajectory do not depend on the slot count
+ * (every trajectory's solve is independent of what else is in flight).  0 (default) = one slot per trajectory. */
+int frx_batch_set_solver_slots(frx_batch *b, int slots);
+
 /* Arg-min of final_cost over the trajectories of this batch (ties -> lowest index).
  * Device-side reduction; the cross-GPU gather is the caller's (NCCL all-gather of 16 B/rank). */
 int frx_batch_argmin(frx_batch *b, int *best_traj, double *best_cost);

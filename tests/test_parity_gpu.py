@@ -338,17 +338,20 @@ def test_vector_free_direction_matches_two_loop_recursion(monkeypatch):
 
 
 def test_solver_reference_tolerance_within_sensitivity_band(oracle_mod):
-    """At the reference's own delta = 1e-5 the GPU result lies inside the oracle's ulp-perturbation band."""
+    """At the reference's own delta = 1e-5 the GPU result lies inside the oracle's ulp-perturbation band.  The band is
+    taken over 24 perturbed oracle solves: the delta test stops on plateaus, and the plateau a solve stops on depends on
+    its rounding path — on the second trajectory here the ORACLE's own final costs under 1-ulp perturbations of the start
+    point spread over 4678 ... 4768 (2 %), with most runs near the lower end, so a 6-run band misses the upper cluster."""
     probs = synth.make_batch(60, 4, 8, 12, 16)
     batch = api.Batch(probs)
     tol = 1e-5
     r = batch.optimize(tol)
     assert (r["status"] >= 0).all()
     for i, o in _oracles(oracle_mod, batch, probs):
-        lo, hi = _oracle_band(oracle_mod, o, tol, runs=6)
+        lo, hi = _oracle_band(oracle_mod, o, tol, runs=24)
         mid = 0.5 * (lo + hi)
         band = max(hi - lo, 2e-3 * mid)  # the oracle's own spread under ulp perturbations (floor 0.2 %)
-        assert abs(r["final_cost"][i] - mid) <= 3 * band, (i, r["final_cost"][i], lo, hi)
+        assert abs(r["final_cost"][i] - mid) <= 1.5 * band, (i, r["final_cost"][i], lo, hi)
     batch.close()
 
 
@@ -423,6 +426,31 @@ def test_solver_statuses_and_masking(oracle_mod):
         if i == 0:
             assert abs(f - o.optimize(1e-5)["final_cost"]) <= 1e-6 * f  # one variable: the minimum itself is well defined
     batch.close()
+
+
+def test_solver_slots_do_not_change_results():
+    """Queue-fed solver slots (frx_batch_set_solver_slots): every trajectory's solve is independent of what else is in flight,
+    so the iterates, statuses and evaluation counts are bit-identical whether 24 ragged trajectories get a slot each or share
+    1, 5 or 23 slots — in both builds of the device code.  Evaluating afterwards sees no stale slot list."""
+    probs = [synth.make_problem(300 + i, 2 + (5 * i) % 11, 6 + i % 5, 8 + 4 * (i % 3)) for i in range(24)]
+    for exact in (0, 1):
+        batch = api.Batch(probs)
+        batch.set_reference_order(exact)
+        ref = batch.optimize(1e-5)
+        assert (ref["evaluations"] > 0).all()
+        for slots in (1, 5, 23, 24, 100):
+            batch.set_solver_slots(slots)
+            r = batch.optimize(1e-5)
+            for k in ("x", "status", "iterations", "evaluations", "final_cost", "durations", "coeffs", "jerk_cost"):
+                assert np.array_equal(ref[k], r[k]), (exact, slots, k)
+            if slots < 24:  # fewer slots than trajectories: waves follow each other
+                assert r["ticks"] >= ref["ticks"] and (slots > 5 or r["ticks"] > ref["ticks"])
+        x = batch.initial_guess()
+        c1, g1 = batch.eval(x)
+        batch.set_solver_slots(0)
+        c2, g2 = batch.eval(x)
+        assert np.array_equal(c1, c2) and np.array_equal(g1, g2) and np.isfinite(c1).all()
+        batch.close()
 
 
 # ---- properties at BASELINE.json's full sizes (C4: 1024 x 64 x 33 x 12) ---------------------------
