@@ -328,12 +328,14 @@ def load_profile_json(name):
         return None
 
 
-def solve_leg(cx, api, probs, tol, first_global, label):
-    """Batched L-BFGS solves of `probs` on this rank + the cross-rank arg-min.  Returns the record (rank-agnostic values)."""
+def solve_leg(cx, api, probs, tol, first_global, label, slots=0):
+    """Batched L-BFGS solves of `probs` on this rank + the cross-rank arg-min.  Returns the record (rank-agnostic values).
+    slots > 0: queue-fed solver slots (frx_batch_set_solver_slots) — `slots` trajectories in flight, the rest wait their turn."""
     t_c = time.perf_counter()
     sbatch = api.Batch(probs, device=cx.local_rank)
     create_ms = (time.perf_counter() - t_c) * 1e3  # V-polytope extraction (device), tables, packing, uploads
     sb = sbatch.count
+    sbatch.set_solver_slots(slots)
     cx.sync_all()
     t0 = time.perf_counter()
     r = sbatch.optimize(tol)
@@ -341,7 +343,8 @@ def solve_leg(cx, api, probs, tol, first_global, label):
     bi, bc = sbatch.argmin()
     best_c, best_i, gather_ms = cx.argmin_gather(bc, first_global + bi)
     wall_max = cx.max_over_ranks([wall])[0]
-    rec = {"workload": label, "value": sb * cx.world / wall_max, "unit": "solves/s", "batch_per_gpu": sb, "rel_tol": tol,
+    rec = {"workload": label, "value": sb * cx.world / wall_max, "unit": "solves/s", "batch_per_gpu": sb,
+           "solver_slots_per_gpu": slots if 0 < slots < sb else sb, "rel_tol": tol,
            "batch_create_ms": create_ms,
            "wall_s_max_over_ranks": wall_max, "device_ms": r["device_ms"], "ticks": int(r["ticks"]),
            "iterations_mean": float(r["iterations"].mean()), "evaluations_mean": float(r["evaluations"].mean()),
@@ -491,6 +494,14 @@ def main():
 
     extras = {}
     if not a.no_extras:
+        if a.solve_batch > 0 and B > a.solve_batch:
+            # the whole C4 batch solved at once (one slot per trajectory), and the same batch fed through half as many slots:
+            # per-trajectory results are identical (tests/test_parity_gpu.py::test_solver_slots_do_not_change_results)
+            extras["solves_full_batch"] = solve_leg(cx, api, probs, 1e-5, rank * a.batch,
+                                                    f"C4: {B} trajectories/GPU x {M} pieces x K={a.samples}, one solver slot each")
+            extras["solves_queue"] = solve_leg(cx, api, probs, 1e-5, rank * a.batch,
+                                               f"C4: {B} trajectories/GPU x {M} pieces x K={a.samples} through {B // 2} solver slots",
+                                               slots=B // 2)
         # ---- strong scaling: north_star's "1024-trajectory x 64-piece x 32-sample batch" in TOTAL over the N ranks ----
         total = a.batch
         per = total // world

@@ -22,6 +22,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  "r"(a)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
     asm volatile(

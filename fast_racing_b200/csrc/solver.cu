@@ -258,7 +258,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                                       const double* __restrict__ Y, double* ysv, double* dyn UPD_MARK_ARG) {
     __shared__ double sg[128], yg[128], cb[128], ca[128], tv[128], al[128];
     __shared__ double sh_gamma;
-    __shared__ unsigned long long full_bar[UPD_NST_MAX];
+    __shared__ unsigned long long full_bar[UPD_NST_MAX], empty_bar[UPD_NST_MAX];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double* SY = sv.SY + (size_t)b * m * m;
     double* SYT = sv.SYT + (size_t)b * m * m;
@@ -286,7 +286,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
         if (tid == 0) {
 #pragma unroll
             for (int i = 0; i < UPD_NST_MAX; i++)
-                if (i < NST) mbar_init(full_bar + i, 1);
+                if (i < NST) mbar_init(full_bar + i, 1), mbar_init(empty_bar + i, UPD_THREADS / 32);
         }
         for (int i = tid; i < n; i += UPD_THREADS) vec[i] = yn[i], vec[nv + i] = sn[i], vec[2 * nv + i] = g[i];
         // rows `end` of S and Y were stored by this CTA a moment ago (generic proxy); the bulk copies below read them through
@@ -321,12 +321,18 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 }
             }
         };
+        // Ring protocol: a stage is released by its eight consumer warps through an "empty" mbarrier (one arrival per warp), and
+        // lane 0 of warp 0 refills the stage of chunk q - 1 at the top of iteration q — the warps meet at a CTA barrier only
+        // where their partial tiles are combined (once per row block and array), not once per chunk.
         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: the DMMAs of a tile alternate between them
         for (int q = 0; q < Q1; q++) {
             const int stg = q % NST;
             const int ct = q % hs.CT, ga = q / hs.CT;
+            if (tid == 0 && q >= 1 && q - 1 + NST < Q1) {
+                mbar_wait(empty_bar + (q - 1) % NST, ((q - 1) / NST) & 1);
+                hist_issue_tile(hs, q - 1 + NST, q - 1 + NST);
+            }
             mbar_wait(full_bar + stg, (q / NST) & 1);
-            if (ct == 0 && ga > 0) flush(ga - 1);
             const int col0 = ct * hs.W, wt = min(hs.W, ld - col0);
             const int rows = min(8, bound - (ga >> 1) * 8);
             const int kper = ((((wt + 7) >> 3) + 7) >> 3) << 3, KS2 = kper >> 3;  // columns per warp: a multiple of 8
@@ -345,6 +351,8 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 dmma_884(c0, c1, av, bv);
                 dmma_884(e0, e1, aw, bw);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + stg);  // this warp is done with the stage
             if (ct == hs.CT - 1) {
                 double* pw = part + (size_t)(ga & 1) * (8 * 8 * 3) + warp * (8 * 3);
                 if (rok) {
@@ -352,12 +360,12 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                     if ((lane & 3) == 1) pw[gid * 3 + 2] = c0 + e0;
                 }
                 c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+                __syncthreads();  // the eight partial tiles of the group are complete (the buffer of parity ga & 1 is next written two groups on)
+                flush(ga);
             }
-            __syncthreads();  // every thread is done with this stage (refill it); the partial tiles of a finished group are complete
-            if (tid == 0 && q + NST < Q1) hist_issue_tile(hs, q + NST, q + NST);
         }
-        flush(Q1 / hs.CT - 1);
-        // the first chunks of pass 2 are requested now and arrive under the two recursions
+        // the first chunks of pass 2 are requested now and arrive under the two recursions (the group barrier above was passed
+        // by every warp after its last tile: all stages are free)
         if (tid == 0)
             for (int j = 0; j < min(NST, Q2); j++) hist_issue_rows(hs, Q1 + j, Q2 - 1 - j);
     } else
@@ -463,6 +471,10 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
         for (int e = 0; e < UPD_COLS; e++) acc[e] = (tid + e * UPD_THREADS < n) ? dg * vec[2 * nv + tid + e * UPD_THREADS] : 0.0;
         for (int j = 0; j < Q2; j++) {
             const int seq = Q1 + j, q = Q2 - 1 - j, stg = seq % NST;
+            if (tid == 0 && j >= 1 && j - 1 + NST < Q2) {
+                mbar_wait(empty_bar + (seq - 1) % NST, ((seq - 1) / NST) & 1);
+                hist_issue_rows(hs, seq - 1 + NST, q + 1 - NST);
+            }
             mbar_wait(full_bar + stg, (seq / NST) & 1);
             const int r0 = (q >> 1) * hs.R2, rows = min(hs.R2, bound - r0);
             const double* chunk = dyn + (size_t)stg * hs.ch;
@@ -474,8 +486,8 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 for (int e = 0; e < UPD_COLS; e++)
                     if (tid + e * UPD_THREADS < n) acc[e] += co * chunk[(size_t)r * ld + tid + e * UPD_THREADS];
             }
-            __syncthreads();
-            if (tid == 0 && j + NST < Q2) hist_issue_rows(hs, seq + NST, q - NST);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + stg);
         }
 #pragma unroll
         for (int e = 0; e < UPD_COLS; e++)

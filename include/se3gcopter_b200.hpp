@@ -449,6 +449,8 @@ public:
         if (best_cost) *best_cost = c;
         return idx;
     }
+    // Keep `slots` candidates in flight and feed the others through as slots free up (0: all at once); results do not change.
+    int setSolverSlots(int slots) { return frx_batch_set_solver_slots(h, slots); }
     frx_batch* handle() { return h; }
 };
 
