@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 
 
 #ifdef FRX_EXACT
@@ -900,10 +901,21 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
                     break;
                 }
             }
-            if (sv.upd_smem &&
-                cudaFuncSetAttribute(lbfgs_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sv.upd_smem) != cudaSuccess) {
-                delete s;
-                return FRX_ERR_CUDA;
+            if (sv.upd_smem) {
+                // the attribute is per function and per device, shared by every solver of the process: only ever raise it
+                // (a second, smaller batch must not lower the limit under a larger one that is still alive)
+                static std::mutex mu;
+                static int cur[64];
+                int dev = 0;
+                cudaGetDevice(&dev);
+                std::lock_guard<std::mutex> lock(mu);
+                if (dev >= 0 && dev < 64 && sv.upd_smem > cur[dev]) {
+                    if (cudaFuncSetAttribute(lbfgs_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sv.upd_smem) != cudaSuccess) {
+                        delete s;
+                        return FRX_ERR_CUDA;
+                    }
+                    cur[dev] = sv.upd_smem;
+                }
             }
         }
     }

@@ -144,6 +144,22 @@ def test_batches_of_different_shapes_coexist(oracle_mod):
     bb.close()
 
 
+def test_solvers_of_different_shapes_coexist():
+    """The update kernel's dynamic shared-memory limit (ring of the streamed history) is per function and process-global too:
+    a solver created later for SMALLER trajectories must not lower it under a live larger one.  Solves are deterministic, so
+    the larger batch must reproduce its own result bit for bit afterwards."""
+    big = api.Batch(synth.make_batch(400, 3, 40, 12, 16))
+    r0 = big.optimize(1e-4)
+    small = api.Batch(synth.make_batch(410, 2, 3, 8, 8))
+    rs = small.optimize(1e-4)
+    assert np.isfinite(rs["final_cost"]).all()
+    r1 = big.optimize(1e-4)
+    for k in ("x", "status", "iterations", "evaluations", "final_cost"):
+        assert np.array_equal(r0[k], r1[k]), k
+    small.close()
+    big.close()
+
+
 def test_device_vpolytope_extraction_matches_host_path(oracle_mod):
     """SURVEY §8(f-1): frx_batch_create extracts the V-polytopes of all corridors in one kernel launch (one warp per polytope);
     the result is bit-identical — vertices AND order — to the host enumeration (same algorithm, geometry_core.hpp), equals the
