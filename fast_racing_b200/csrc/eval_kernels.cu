@@ -69,7 +69,21 @@ __device__ __forceinline__ void cta_bar64() { asm volatile("bar.sync 1, 64;" :::
 // Phase clocks (debug builds only: FRX_NVCC_EXTRA=-DFRX_PHASE_CLK): lane 0 of each warp of one CTA records clock64()
 // at phase boundaries; scripts/phase_clocks.py prints the differences.  Slot = kernel*32 + warp*16 + mark.
 __device__ long long g_phase_clk[96];
+// Per-CTA wall spans (debug builds): globaltimer (ns) and SM id at the first and last PHASE_MARK of K1 (kernel 0) / K3 (2),
+// for every CTA of the grid: shows launch skew, waves and per-SM crowding (scripts/cta_spans.py).
+__device__ unsigned long long g_cta_span[2][3][4096];
 #ifdef FRX_PHASE_CLK
+__device__ __forceinline__ void cta_span_mark(int kernel, int which) {
+    if (threadIdx.x == 0 && blockIdx.x < 4096) {
+        unsigned long long t;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_cta_span[kernel ? 1 : 0][which][blockIdx.x] = t;
+        if (which == 0) g_cta_span[kernel ? 1 : 0][2][blockIdx.x] = sm;
+    }
+}
+#define CTA_SPAN(kernel, which) cta_span_mark(kernel, which)
 #define PHASE_MARK(kernel, mark)                                                                          \
     do {                                                                                                  \
         if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 0)                                       \
@@ -108,6 +122,9 @@ __device__ long long g_phase_clk[96];
     } while (0)
 #define PHASE_MARK(kernel, mark) \
     do {                         \
+    } while (0)
+#define CTA_SPAN(kernel, which) \
+    do {                        \
     } while (0)
 #endif
 
@@ -1404,6 +1421,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     double* nR = nL + 4 * M;
     double* nG = nR + 6 * M;
     int* wpi = reinterpret_cast<int*>(nG + 4 * M);
+    CTA_SPAN(0, 0);
     PHASE_MARK(0, 0);
 
     // this trajectory's x and vertex ranges -> L2, one bulk prefetch each, issued before anything depends on them
@@ -1609,6 +1627,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
         double* cg = bv.c + 18 * (size_t)(p0 + i) + d;
         cg[0] = P0, cg[3] = V0, cg[6] = 0.5 * A0, cg[9] = c3, cg[12] = c4, cg[15] = c5;
     }
+    CTA_SPAN(0, 1);
     PHASE_MARK(0, 5);
 }
 
@@ -1656,6 +1675,7 @@ __global__ void __launch_bounds__(64)
     int* ioff = ivs + coarseN;
     int* wpi = ioff + coarseN;
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm + backward_smem_doubles(M, coarseN) - 1);
+    CTA_SPAN(2, 0);
     PHASE_MARK(2, 0);
 
     const double* tailst = bv.headtail + 18 * (size_t)b + 9;  // tail p (0..2), v (3..5), a (6..8)
@@ -1936,6 +1956,7 @@ __global__ void __launch_bounds__(64)
             }
         }
     }
+    CTA_SPAN(2, 1);
     PHASE_MARK(2, 7);
 }
 #endif  // !FRX_EXACT (reduced-system kernels)
@@ -2141,4 +2162,5 @@ double measure_fp64_tflops() {
 }
 
 cudaError_t fetch_phase_clocks(long long* out96) { return cudaMemcpyFromSymbol(out96, g_phase_clk, sizeof(long long) * 96); }
+cudaError_t fetch_cta_spans(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_cta_span, sizeof(unsigned long long) * 2 * 3 * 4096); }
 }  // namespace FRX_IMPL

@@ -42,6 +42,7 @@
                              const double* x_dev, double* cost_dev, double* grad_dev, cudaStream_t st, int reps, double* ms);      \
     double measure_fp64_tflops();                                                                                                  \
     cudaError_t fetch_phase_clocks(long long* out96);                                                                              \
+    cudaError_t fetch_cta_spans(unsigned long long* out);                                                                          \
     }
 FRX_DECLARE_EVAL_API(frx_fast)
 FRX_DECLARE_EVAL_API(frx_exact)
@@ -868,6 +869,12 @@ int frx_batch_profile_eval(frx_batch* b, const double* x_dev, double* cost_dev, 
 int frx_debug_phase_clocks(long long* out96) {
     if (!out96) return FRX_ERR_INVALID_ARG;
     CK(frx_fast::fetch_phase_clocks(out96));
+    return FRX_OK;
+}
+// Debug builds: per-CTA globaltimer spans of K1 / K3, out[2][3][4096] = {kernel}{start ns, end ns, SM id}{block}.
+int frx_debug_cta_spans(unsigned long long* out) {
+    if (!out) return FRX_ERR_INVALID_ARG;
+    CK(frx_fast::fetch_cta_spans(out));
     return FRX_OK;
 }
 int frx_debug_update_clocks(long long* out16, int reset) {
