@@ -1386,10 +1386,99 @@ __global__ void __launch_bounds__(64)
 // Derivation and a numpy check against a dense restatement of the reference system: scripts/proto/reduced_minco.py.
 // =================================================================================================
 // shared memory of minco_backward_kernel in doubles (layout in its header comment); the last slot is the mbarrier
-__host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
-    return (size_t)55 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
+// Parallel cyclic reduction of the reduced MINCO system  A_j y_{j-1} + D_j y_j + A_{j+1}^T y_{j+1} = r_j  (nodes j = 1..N, 2 x 2
+// blocks, symmetric positive definite; three right-hand sides = the axes), one thread per node (N <= PCR_MAX_NODES = the CTA):
+// at stride s every node eliminates its neighbours j -+ s at once,
+//   alpha = -A_j Dinv_{j-s},  gamma = -A_{j+s}^T Dinv_{j+s},
+//   D_j += alpha A_j^T + gamma A_{j+s},   A_j := alpha A_{j-s},   r_j += alpha r_{j-s} + gamma r_{j+s}
+// (the reduced matrices stay symmetric, so the upper coupling is never stored: C_j = A_{j+s}^T), and after ceil(log2 N) strides
+// y_j = Dinv_j r_j.  Six dependent rounds of ~70 fp64 instructions per thread for 64 pieces, against the 63-node chain of the
+// block LDL^T (three active lanes, ~320 cycles per node) — scripts/proto/pcr_reduced.py is the numpy emulation of this slot
+// algebra (1e-13 of a dense solve with durations spread over two decades).  In place on shared arrays indexed by node:
+// D[3j..] (d11 d12 d22), A[4j..] (row-major; A_1 is taken as zero: the head state is folded into r_1), R[6j + d] / R[6j+3+d]
+// (velocity / acceleration rows, axis d), Iv[4j..] (scratch: the inverse blocks).  Every thread of the 64-thread CTA calls it.
+#define PCR_MAX_NODES 64
+template <int DS, int AS>  // strides of D and A in doubles per node (K1: separate arrays 3 / 4; K3: both inside the 8-double node record)
+__device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, double* Iv, double* Yout, int N, int tid) {
+    const int j = tid + 1;
+    const bool on = j <= N;
+    double d11 = 1.0, d12 = 0.0, d22 = 1.0, a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
+    double r[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double i11 = 0.0, i12 = 0.0, i22 = 0.0;
+    if (on) {
+        d11 = D[DS * j], d12 = D[DS * j + 1], d22 = D[DS * j + 2];
+        if (j > 1) a11 = A[AS * j], a12 = A[AS * j + 1], a21 = A[AS * j + 2], a22 = A[AS * j + 3];
+#pragma unroll
+        for (int q = 0; q < 6; q++) r[q] = R[6 * j + q];
+        const double id = fast_rcp3(fma(d11, d22, -(d12 * d12)));
+        i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;
+        Iv[3 * j] = i11, Iv[3 * j + 1] = i12, Iv[3 * j + 2] = i22;
+        A[AS * j] = a11, A[AS * j + 1] = a12, A[AS * j + 2] = a21, A[AS * j + 3] = a22;  // A_1 := 0 for the neighbours
+    }
+    __syncthreads();
+    for (int s = 1; s < N; s <<= 1) {
+        double n11 = d11, n12 = d12, n22 = d22, b11 = 0.0, b12 = 0.0, b21 = 0.0, b22 = 0.0;
+        if (on) {
+            const int lo = j - s, hi = j + s;
+            if (lo >= 1) {
+                const double l11 = Iv[3 * lo], l12 = Iv[3 * lo + 1], l22 = Iv[3 * lo + 2];
+                const double al11 = -fma(a11, l11, a12 * l12), al12 = -fma(a11, l12, a12 * l22);
+                const double al21 = -fma(a21, l11, a22 * l12), al22 = -fma(a21, l12, a22 * l22);
+                n11 = fma(al11, a11, fma(al12, a12, n11));
+                n12 = fma(al11, a21, fma(al12, a22, n12));
+                n22 = fma(al21, a21, fma(al22, a22, n22));
+                const double c11 = A[AS * lo], c12 = A[AS * lo + 1], c21 = A[AS * lo + 2], c22 = A[AS * lo + 3];
+                b11 = fma(al11, c11, al12 * c21), b12 = fma(al11, c12, al12 * c22);
+                b21 = fma(al21, c11, al22 * c21), b22 = fma(al21, c12, al22 * c22);
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double rv = R[6 * lo + d], ra = R[6 * lo + 3 + d];
+                    r[d] = fma(al11, rv, fma(al12, ra, r[d]));
+                    r[3 + d] = fma(al21, rv, fma(al22, ra, r[3 + d]));
+                }
+            }
+            if (hi <= N) {
+                const double h11 = A[AS * hi], h12 = A[AS * hi + 1], h21 = A[AS * hi + 2], h22 = A[AS * hi + 3];
+                const double u11 = Iv[3 * hi], u12 = Iv[3 * hi + 1], u22 = Iv[3 * hi + 2];
+                const double g11 = -fma(h11, u11, h21 * u12), g12 = -fma(h11, u12, h21 * u22);  // gamma = -A_hi^T Dinv_hi
+                const double g21 = -fma(h12, u11, h22 * u12), g22 = -fma(h12, u12, h22 * u22);
+                n11 = fma(g11, h11, fma(g12, h21, n11));
+                n12 = fma(g11, h12, fma(g12, h22, n12));
+                n22 = fma(g21, h12, fma(g22, h22, n22));
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double rv = R[6 * hi + d], ra = R[6 * hi + 3 + d];
+                    r[d] = fma(g11, rv, fma(g12, ra, r[d]));
+                    r[3 + d] = fma(g21, rv, fma(g22, ra, r[3 + d]));
+                }
+            }
+        }
+        __syncthreads();  // every node has read its neighbours
+        if (on) {
+            d11 = n11, d12 = n12, d22 = n22, a11 = b11, a12 = b12, a21 = b21, a22 = b22;
+            const double id = fast_rcp3(fma(d11, d22, -(d12 * d12)));
+            i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;
+            Iv[3 * j] = i11, Iv[3 * j + 1] = i12, Iv[3 * j + 2] = i22;
+            A[AS * j] = a11, A[AS * j + 1] = a12, A[AS * j + 2] = a21, A[AS * j + 3] = a22;
+#pragma unroll
+            for (int q = 0; q < 6; q++) R[6 * j + q] = r[q];
+        }
+        __syncthreads();
+    }
+    if (on) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            Yout[6 * j + d] = fma(i11, r[d], i12 * r[3 + d]);
+            Yout[6 * j + 3 + d] = fma(i12, r[d], i22 * r[3 + d]);
+        }
+    }
 }
-#define NODE_F 8  // doubles per node kept in bv.lu for K3: [0..2] inverse pivot block (i11, i12, i22), [3..6] G_j = L_j Di_{j-1}
+
+__host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
+    return (size_t)56 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
+}
+#define NODE_F 8  // doubles per node kept in bv.lu for K3.  Up to PCR_MAX_NODES + 1 pieces: [0..2] D_j (d11, d12, d22), [3..6] L_j —
+                  // the node blocks themselves (K3 runs its own cyclic reduction); longer: [0..2] inverse pivot block, [3..6] G_j = L_j Di_{j-1}
 
 // K1 (fast) -----------------------------------------------------------------------------------------
 // One trajectory per CTA of two warps.  forwardT / splitToFineT / forwardP (CPU.hpp:626, :930, :729) by all threads, the
@@ -1539,8 +1628,20 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
     __syncthreads();
     PHASE_MARK(0, 2);
 
-    // ---- block LDL^T with the forward substitution fused in, then the back substitution: lanes 0..2 of warp 0 ----
     double* fac = bv.lu + (size_t)NODE_F * p0;
+    if (M - 1 <= PCR_MAX_NODES) {
+        // ---- the reduced system by parallel cyclic reduction (one thread per node).  K3 solves the adjoint system the same way:
+        //      it gets the node blocks themselves (8 doubles per node: D | L | unused) instead of LDL^T factors. ----
+        for (int j = 1 + tid; j < M; j += 64) {
+            double* f = fac + NODE_F * j;
+            f[0] = nD[3 * j], f[1] = nD[3 * j + 1], f[2] = nD[3 * j + 2];
+            f[3] = nL[4 * j], f[4] = nL[4 * j + 1], f[5] = nL[4 * j + 2], f[6] = nL[4 * j + 3];
+        }
+        PHASE_MARK(0, 3);
+        pcr_solve<3, 4>(nD, nL, nR, nG, Y, M - 1, tid);
+    } else
+    // ---- long trajectories: block LDL^T with the forward substitution fused in, then the back substitution: lanes 0..2 of
+    //      warp 0 ----
     if (warp == 0 && lane < 3 && M > 1) {
         const int d = lane;
         double d11 = nD[3], d12 = nD[4], d22 = nD[5];  // pivot block of node 1
@@ -1638,7 +1739,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 // the reference's order, the closed-form dJ/dT and dJ/dq, then mergeToCoarseGradT / addLayerTGrad / addLayerPGrad
 // (CPU.hpp:946, :816, :897).
 // smem (doubles): Ts[M] | iT[M] | SE[18M] (dJ/dc in, then per piece: start part (P,V,A) 9 | end part 9) | CS[18M] (c) |
-//                 fc[8M] (after the sweeps: kt[3M] | gT[M] | gq[3M]) | Z[6M] | gTd[M] | gTc[coarseN+1] | em[2M] | tfac[coarseN] |
+//                 fc[8M] (after the solve: kt[3M] | gT[M] | gq[3M]) | Z[6M] | Iv[3M] | gTd[M] | gTc[coarseN+1] | tfac[coarseN] |
 //                 ivs, ioff [coarseN ints each] | wpi[3M ints] | mbarrier
 __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
@@ -1664,13 +1765,13 @@ __global__ void __launch_bounds__(64)
     double* CS = SE + 18 * (size_t)M;
     double* fc = CS + 18 * (size_t)M;
     double* Z = fc + NODE_F * (size_t)M;
-    double* gTd = Z + 6 * (size_t)M;
+    double* Iv = Z + 6 * (size_t)M;  // scratch of the cyclic reduction (inverse blocks)
+    double* gTd = Iv + 3 * (size_t)M;
     double* kt = fc;  // kt[3M] | gT[M] | gq[3M] reuse the factor block: written only after the sweeps are done with it
     double* gT = kt + 3 * (size_t)M;
     double* gq = gT + M;
     double* gTc = gTd + M;
-    double* em = gTc + coarseN + 1;
-    double* tfac = em + 2 * (size_t)M;
+    double* tfac = gTc + coarseN + 1;
     int* ivs = reinterpret_cast<int*>(tfac + coarseN);
     int* ioff = ivs + coarseN;
     int* wpi = ioff + coarseN;
@@ -1703,6 +1804,63 @@ __global__ void __launch_bounds__(64)
         wpi[i] = bv.wp_vert_cnt[p0 + i] - 1;
         wpi[M + i] = bv.wp_xi_off[p0 + i];
         wpi[2 * M + i] = bv.wp_vert_off[p0 + i];
+    }
+    if (warp == 1) {
+        // ---- cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988) by warp 1 while the bulk copies
+        //      fly: strided partial sums and a fixed shuffle tree (the reference sums sequentially; reference-order mode does
+        //      too), time-map derivative, interval offsets ----
+        double se = 0.0, sp = 0.0, sT = 0.0;
+        for (int i = lane; i < M; i += 32) {
+            se += bv.energy[p0 + i];
+            sp += bv.pen[p0 + i];
+        }
+        for (int i = lane; i < coarseN; i += 32) ivs[i] = bv.intervals[co0 + i];
+        if (par.softT) {
+            for (int i = lane; i < coarseN; i += 32) {  // time map and its derivative (CPU.hpp:639-641, 830-838)
+                const double t = x[i];
+                double Tv, dv;
+                if (par.c2) {
+                    Tv = c2_forward(t);
+                    if (t > 0)
+                        dv = t + 1.0;
+                    else {
+                        const double den = (0.5 * t - 1.0) * t + 1.0;
+                        dv = (1.0 - t) / (den * den);
+                    }
+                } else {
+                    Tv = exp(t);
+                    dv = Tv;
+                }
+                gTc[i] = Tv;
+                tfac[i] = dv;
+                sT += Tv;
+            }
+        } else {
+            for (int i = lane; i < M; i += 32) sT += bv.T[p0 + i];  // fixed total time: rho = 0 anyway
+        }
+        __syncwarp();
+        {
+            int carry = 0;  // exclusive prefix sum of the interval counts, 32 at a time
+            for (int base = 0; base < coarseN; base += 32) {
+                const int i = base + lane;
+                const int v = i < coarseN ? ivs[i] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (i < coarseN) ioff[i] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            sT += __shfl_xor_sync(0xffffffffu, sT, o);
+        }
+        if (lane == 0) cost_out[b] = (se + sp) + par.rho * sT;
     }
     mbar_wait(mbar, 0);
     __syncthreads();
@@ -1742,9 +1900,12 @@ __global__ void __launch_bounds__(64)
     }
     __syncthreads();
     PHASE_MARK(2, 2);
+    const bool use_pcr = M - 1 <= PCR_MAX_NODES;
+    // ---- S mu = dJ/dy: the same cyclic reduction as K1 on the node blocks K1 left in the factor slot (in place over Z) ----
+    if (use_pcr) pcr_solve<NODE_F, NODE_F>(fc, fc + 3, Z, Iv, Z, M - 1, tid);
     if (warp == 0) {
-        // ---- S mu = dJ/dy with K1's factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
-        if (lane < 3 && M > 1) {
+        // ---- long trajectories: with K1's LDL^T factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
+        if (lane < 3 && M > 1 && !use_pcr) {
             const int d = lane;
             // both sweeps are chains of two FMAs per node; the operands of the next node are loaded into registers before
             // this node's results are stored (the stores would otherwise fence the loads: same shared array)
@@ -1791,54 +1952,6 @@ __global__ void __launch_bounds__(64)
                 Z[6 * j + 3 + d] = m1;
             }
         }
-    } else {
-        // ---- meanwhile: cost = sum energy + sum penalty + rho * sum T (CPU.hpp:542,406,988), time-map derivative, tables ----
-        for (int i = lane; i < M; i += 32) {
-            em[i] = bv.energy[p0 + i];
-            em[M + i] = bv.pen[p0 + i];
-        }
-        for (int i = lane; i < coarseN; i += 32) ivs[i] = bv.intervals[co0 + i];
-        if (par.softT) {
-            for (int i = lane; i < coarseN; i += 32) {  // time map and its derivative (CPU.hpp:639-641, 830-838)
-                const double t = x[i];
-                double Tv, dv;
-                if (par.c2) {
-                    Tv = c2_forward(t);
-                    if (t > 0)
-                        dv = t + 1.0;
-                    else {
-                        const double den = (0.5 * t - 1.0) * t + 1.0;
-                        dv = (1.0 - t) / (den * den);
-                    }
-                } else {
-                    Tv = exp(t);
-                    dv = Tv;
-                }
-                gTc[i] = Tv;
-                tfac[i] = dv;
-            }
-        }
-        __syncwarp();
-        double part = 0.0;
-        if (lane == 0) {
-            for (int i = 0; i < M; i++) part += em[i];
-        } else if (lane == 1) {
-            for (int i = 0; i < M; i++) part += em[M + i];
-        } else if (lane == 2) {
-            if (par.softT) {
-                for (int i = 0; i < coarseN; i++) part += gTc[i];
-            } else {
-                for (int i = 0; i < M; i++) part += Ts[i];  // fixed total time: rho = 0 anyway
-            }
-        } else if (lane == 3) {
-            int o = 0;
-            for (int i = 0; i < coarseN; i++) {
-                ioff[i] = o;
-                o += ivs[i];
-            }
-        }
-        const double pn = __shfl_sync(0xffffffffu, part, 1), sT = __shfl_sync(0xffffffffu, part, 2);
-        if (lane == 0) cost_out[b] = (part + pn) + par.rho * sT;
     }
     __syncthreads();
     PHASE_MARK(2, 4);

@@ -508,6 +508,22 @@ def test_c4_batch_order_independence(c4_batch):
     sub.close()
 
 
+def test_c4_fast_mode_agrees_with_reference_order_mode_on_every_trajectory(c4_batch):
+    """Fast mode (reduced system by cyclic reduction, adjoint-vector penalties, tree reductions) against reference-order mode
+    (bit-identical to the reference's own code) on ALL 1024 trajectories of C4, at a perturbed point with every penalty
+    family active: the stated fp64 tolerance of the fast path, not just spot checks."""
+    batch, _ = c4_batch
+    x = batch.initial_guess() + 0.3 * np.random.default_rng(9).normal(size=batch.total_x)
+    c_fast, g_fast = batch.eval(x)
+    batch.set_reference_order(1)
+    c_ref, g_ref = batch.eval(x)
+    batch.set_reference_order(0)
+    rc = np.abs(c_fast - c_ref) / np.abs(c_ref)
+    rg = np.array([rel_err(g_fast[batch.x_off[i]:batch.x_off[i + 1]], g_ref[batch.x_off[i]:batch.x_off[i + 1]]) for i in range(batch.count)])
+    assert np.median(rc) <= 1e-13 and rc.max() <= 5e-11, (np.median(rc), rc.max())
+    assert np.median(rg) <= 1e-12 and rg.max() <= GRAD_RTOL, (np.median(rg), rg.max())
+
+
 def test_c4_gradient_is_the_derivative_of_the_cost(c4_batch):
     """Directional finite differences of the CUDA cost against the CUDA gradient, all 1024 trajectories at once."""
     batch, _ = c4_batch
@@ -517,7 +533,9 @@ def test_c4_gradient_is_the_derivative_of_the_cost(c4_batch):
     for i in range(batch.count):
         s = slice(batch.x_off[i], batch.x_off[i + 1])
         d[s] /= np.linalg.norm(d[s])
-    h = 1e-6
+    # central differences: rounding noise eps_cost * |cost| / h against truncation ~ h^2: the cost carries ~1e-11 relative
+    # rounding in the worst trajectories (cyclic reduction of the MINCO system), so h = 1e-5
+    h = 1e-5
     c0, g0 = batch.eval(x)
     cp, _ = batch.eval(x + h * d)
     cm, _ = batch.eval(x - h * d)
