@@ -1398,8 +1398,14 @@ __global__ void __launch_bounds__(64)
 // D[3j..] (d11 d12 d22), A[4j..] (row-major; A_1 is taken as zero: the head state is folded into r_1), R[6j + d] / R[6j+3+d]
 // (velocity / acceleration rows, axis d), Iv[4j..] (scratch: the inverse blocks).  Every thread of the 64-thread CTA calls it.
 #define PCR_MAX_NODES 64
+#define PCR_STATE 13  // doubles per node that the neighbours read: inverse block (3), lower coupling (4), right-hand sides (6)
+// In: D (stride DS), A (stride AS), R (6 per node) indexed by node j = 1..N.  W: scratch of PCR_STATE * N doubles, may overlap
+// D / A / R (they are read into registers first): the state the neighbours read lives there component-major
+// (W[c * N + j - 1]: consecutive lanes hit consecutive banks; node-major records of 4 or 6 doubles are 8- and
+// 4-way bank conflicts for 8-byte loads).  Out: Yout[6j + d] / Yout[6j + 3 + d], may overlap W.  Every thread of the
+// 64-thread CTA calls it.
 template <int DS, int AS>  // strides of D and A in doubles per node (K1: separate arrays 3 / 4; K3: both inside the 8-double node record)
-__device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, double* Iv, double* Yout, int N, int tid) {
+__device__ __forceinline__ void pcr_solve(const double* D, const double* A, const double* R, double* W, double* Yout, int N, int tid) {
     const int j = tid + 1;
     const bool on = j <= N;
     double d11 = 1.0, d12 = 0.0, d22 = 1.0, a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0;
@@ -1407,39 +1413,48 @@ __device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, doubl
     double i11 = 0.0, i12 = 0.0, i22 = 0.0;
     if (on) {
         d11 = D[DS * j], d12 = D[DS * j + 1], d22 = D[DS * j + 2];
-        if (j > 1) a11 = A[AS * j], a12 = A[AS * j + 1], a21 = A[AS * j + 2], a22 = A[AS * j + 3];
+        if (j > 1) a11 = A[AS * j], a12 = A[AS * j + 1], a21 = A[AS * j + 2], a22 = A[AS * j + 3];  // A_1 := 0
 #pragma unroll
         for (int q = 0; q < 6; q++) r[q] = R[6 * j + q];
         const double id = fast_rcp3(fma(d11, d22, -(d12 * d12)));
         i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;
-        Iv[3 * j] = i11, Iv[3 * j + 1] = i12, Iv[3 * j + 2] = i22;
-        A[AS * j] = a11, A[AS * j + 1] = a12, A[AS * j + 2] = a21, A[AS * j + 3] = a22;  // A_1 := 0 for the neighbours
     }
+    __syncthreads();  // the inputs are in registers: W may overwrite them
+    const int NS = N;
+    double* w = W + tid;  // component c of this node: w[c * NS]
+    auto publish = [&]() {
+        w[0] = i11, w[NS] = i12, w[2 * NS] = i22;
+        w[3 * NS] = a11, w[4 * NS] = a12, w[5 * NS] = a21, w[6 * NS] = a22;
+#pragma unroll
+        for (int q = 0; q < 6; q++) w[(7 + q) * NS] = r[q];
+    };
+    if (on) publish();
     __syncthreads();
     for (int s = 1; s < N; s <<= 1) {
         double n11 = d11, n12 = d12, n22 = d22, b11 = 0.0, b12 = 0.0, b21 = 0.0, b22 = 0.0;
         if (on) {
-            const int lo = j - s, hi = j + s;
-            if (lo >= 1) {
-                const double l11 = Iv[3 * lo], l12 = Iv[3 * lo + 1], l22 = Iv[3 * lo + 2];
+            if (j - s >= 1) {
+                const double* lo = w - s;
+                const double l11 = lo[0], l12 = lo[NS], l22 = lo[2 * NS];
                 const double al11 = -fma(a11, l11, a12 * l12), al12 = -fma(a11, l12, a12 * l22);
                 const double al21 = -fma(a21, l11, a22 * l12), al22 = -fma(a21, l12, a22 * l22);
                 n11 = fma(al11, a11, fma(al12, a12, n11));
                 n12 = fma(al11, a21, fma(al12, a22, n12));
                 n22 = fma(al21, a21, fma(al22, a22, n22));
-                const double c11 = A[AS * lo], c12 = A[AS * lo + 1], c21 = A[AS * lo + 2], c22 = A[AS * lo + 3];
+                const double c11 = lo[3 * NS], c12 = lo[4 * NS], c21 = lo[5 * NS], c22 = lo[6 * NS];
                 b11 = fma(al11, c11, al12 * c21), b12 = fma(al11, c12, al12 * c22);
                 b21 = fma(al21, c11, al22 * c21), b22 = fma(al21, c12, al22 * c22);
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    const double rv = R[6 * lo + d], ra = R[6 * lo + 3 + d];
+                    const double rv = lo[(7 + d) * NS], ra = lo[(10 + d) * NS];
                     r[d] = fma(al11, rv, fma(al12, ra, r[d]));
                     r[3 + d] = fma(al21, rv, fma(al22, ra, r[3 + d]));
                 }
             }
-            if (hi <= N) {
-                const double h11 = A[AS * hi], h12 = A[AS * hi + 1], h21 = A[AS * hi + 2], h22 = A[AS * hi + 3];
-                const double u11 = Iv[3 * hi], u12 = Iv[3 * hi + 1], u22 = Iv[3 * hi + 2];
+            if (j + s <= N) {
+                const double* hi = w + s;
+                const double h11 = hi[3 * NS], h12 = hi[4 * NS], h21 = hi[5 * NS], h22 = hi[6 * NS];
+                const double u11 = hi[0], u12 = hi[NS], u22 = hi[2 * NS];
                 const double g11 = -fma(h11, u11, h21 * u12), g12 = -fma(h11, u12, h21 * u22);  // gamma = -A_hi^T Dinv_hi
                 const double g21 = -fma(h12, u11, h22 * u12), g22 = -fma(h12, u12, h22 * u22);
                 n11 = fma(g11, h11, fma(g12, h21, n11));
@@ -1447,7 +1462,7 @@ __device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, doubl
                 n22 = fma(g21, h12, fma(g22, h22, n22));
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    const double rv = R[6 * hi + d], ra = R[6 * hi + 3 + d];
+                    const double rv = hi[(7 + d) * NS], ra = hi[(10 + d) * NS];
                     r[d] = fma(g11, rv, fma(g12, ra, r[d]));
                     r[3 + d] = fma(g21, rv, fma(g22, ra, r[3 + d]));
                 }
@@ -1458,10 +1473,7 @@ __device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, doubl
             d11 = n11, d12 = n12, d22 = n22, a11 = b11, a12 = b12, a21 = b21, a22 = b22;
             const double id = fast_rcp3(fma(d11, d22, -(d12 * d12)));
             i11 = d22 * id, i12 = -(d12 * id), i22 = d11 * id;
-            Iv[3 * j] = i11, Iv[3 * j + 1] = i12, Iv[3 * j + 2] = i22;
-            A[AS * j] = a11, A[AS * j + 1] = a12, A[AS * j + 2] = a21, A[AS * j + 3] = a22;
-#pragma unroll
-            for (int q = 0; q < 6; q++) R[6 * j + q] = r[q];
+            if ((s << 1) < N) publish();  // nobody reads the state after the last round
         }
         __syncthreads();
     }
@@ -1475,7 +1487,7 @@ __device__ __forceinline__ void pcr_solve(double* D, double* A, double* R, doubl
 }
 
 __host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
-    return (size_t)56 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
+    return (size_t)53 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
 }
 #define NODE_F 8  // doubles per node kept in bv.lu for K3.  Up to PCR_MAX_NODES + 1 pieces: [0..2] D_j (d11, d12, d22), [3..6] L_j —
                   // the node blocks themselves (K3 runs its own cyclic reduction); longer: [0..2] inverse pivot block, [3..6] G_j = L_j Di_{j-1}
@@ -1638,7 +1650,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
             f[3] = nL[4 * j], f[4] = nL[4 * j + 1], f[5] = nL[4 * j + 2], f[6] = nL[4 * j + 3];
         }
         PHASE_MARK(0, 3);
-        pcr_solve<3, 4>(nD, nL, nR, nG, Y, M - 1, tid);
+        pcr_solve<3, 4>(nD, nL, nR, nD, Y, M - 1, tid);  // scratch: the node-block arrays themselves (17 M doubles >= 13 (M - 1))
     } else
     // ---- long trajectories: block LDL^T with the forward substitution fused in, then the back substitution: lanes 0..2 of
     //      warp 0 ----
@@ -1739,7 +1751,7 @@ __global__ void __launch_bounds__(64) minco_forward_kernel(BatchView bv, const d
 // the reference's order, the closed-form dJ/dT and dJ/dq, then mergeToCoarseGradT / addLayerTGrad / addLayerPGrad
 // (CPU.hpp:946, :816, :897).
 // smem (doubles): Ts[M] | iT[M] | SE[18M] (dJ/dc in, then per piece: start part (P,V,A) 9 | end part 9) | CS[18M] (c) |
-//                 fc[8M] (after the solve: kt[3M] | gT[M] | gq[3M]) | Z[6M] | Iv[3M] | gTd[M] | gTc[coarseN+1] | tfac[coarseN] |
+//                 fc[8M] (after the solve: kt[3M] | gT[M] | gq[3M]) | Z[6M] | gTd[M] | gTc[coarseN+1] | tfac[coarseN] |
 //                 ivs, ioff [coarseN ints each] | wpi[3M ints] | mbarrier
 __global__ void __launch_bounds__(64)
     minco_backward_kernel(BatchView bv, const double* __restrict__ xin, double* __restrict__ cost_out,
@@ -1765,8 +1777,7 @@ __global__ void __launch_bounds__(64)
     double* CS = SE + 18 * (size_t)M;
     double* fc = CS + 18 * (size_t)M;
     double* Z = fc + NODE_F * (size_t)M;
-    double* Iv = Z + 6 * (size_t)M;  // scratch of the cyclic reduction (inverse blocks)
-    double* gTd = Iv + 3 * (size_t)M;
+    double* gTd = Z + 6 * (size_t)M;
     double* kt = fc;  // kt[3M] | gT[M] | gq[3M] reuse the factor block: written only after the sweeps are done with it
     double* gT = kt + 3 * (size_t)M;
     double* gq = gT + M;
@@ -1902,7 +1913,7 @@ __global__ void __launch_bounds__(64)
     PHASE_MARK(2, 2);
     const bool use_pcr = M - 1 <= PCR_MAX_NODES;
     // ---- S mu = dJ/dy: the same cyclic reduction as K1 on the node blocks K1 left in the factor slot (in place over Z) ----
-    if (use_pcr) pcr_solve<NODE_F, NODE_F>(fc, fc + 3, Z, Iv, Z, M - 1, tid);
+    if (use_pcr) pcr_solve<NODE_F, NODE_F>(fc, fc + 3, Z, fc, Z, M - 1, tid);  // scratch: fc | Z (14 M doubles >= 13 (M - 1))
     if (warp == 0) {
         // ---- long trajectories: with K1's LDL^T factors: z_j = b_j - G_j z_{j-1},  w_j = Di_j z_j,  mu_j = w_j - G_{j+1}^T mu_{j+1} ----
         if (lane < 3 && M > 1 && !use_pcr) {
