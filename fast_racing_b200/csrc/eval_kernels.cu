@@ -1385,7 +1385,6 @@ __global__ void __launch_bounds__(64)
 //                   + jerk_c jerk_ct - snap_ct.a_{i+1} - snap_c.muA_{i+1} + crackle_ct.v_{i+1} + crackle_c.muV_{i+1}  at t = T_i.
 // Derivation and a numpy check against a dense restatement of the reference system: scripts/proto/reduced_minco.py.
 // =================================================================================================
-// shared memory of minco_backward_kernel in doubles (layout in its header comment); the last slot is the mbarrier
 // Parallel cyclic reduction of the reduced MINCO system  A_j y_{j-1} + D_j y_j + A_{j+1}^T y_{j+1} = r_j  (nodes j = 1..N, 2 x 2
 // blocks, symmetric positive definite; three right-hand sides = the axes), one thread per node (N <= PCR_MAX_NODES = the CTA):
 // at stride s every node eliminates its neighbours j -+ s at once,
@@ -1394,9 +1393,8 @@ __global__ void __launch_bounds__(64)
 // (the reduced matrices stay symmetric, so the upper coupling is never stored: C_j = A_{j+s}^T), and after ceil(log2 N) strides
 // y_j = Dinv_j r_j.  Six dependent rounds of ~70 fp64 instructions per thread for 64 pieces, against the 63-node chain of the
 // block LDL^T (three active lanes, ~320 cycles per node) — scripts/proto/pcr_reduced.py is the numpy emulation of this slot
-// algebra (1e-13 of a dense solve with durations spread over two decades).  In place on shared arrays indexed by node:
-// D[3j..] (d11 d12 d22), A[4j..] (row-major; A_1 is taken as zero: the head state is folded into r_1), R[6j + d] / R[6j+3+d]
-// (velocity / acceleration rows, axis d), Iv[4j..] (scratch: the inverse blocks).  Every thread of the 64-thread CTA calls it.
+// algebra (1e-13 of a dense solve with durations spread over two decades).  Blocks: D (d11 d12 d22), A (row-major; A_1 is taken
+// as zero: the head state is folded into r_1), R[6j + d] / R[6j + 3 + d] (velocity / acceleration rows, axis d).
 #define PCR_MAX_NODES 64
 #define PCR_STATE 13  // doubles per node that the neighbours read: inverse block (3), lower coupling (4), right-hand sides (6)
 // In: D (stride DS), A (stride AS), R (6 per node) indexed by node j = 1..N.  W: scratch of PCR_STATE * N doubles, may overlap
@@ -1486,6 +1484,7 @@ __device__ __forceinline__ void pcr_solve(const double* D, const double* A, cons
     }
 }
 
+// shared memory of minco_backward_kernel in doubles (layout in its header comment); the last slot is the mbarrier
 __host__ __device__ inline size_t backward_smem_doubles(int M, int coarseN) {
     return (size_t)53 * M + 2 * (size_t)coarseN + 1 + (2 * (size_t)coarseN + 3 * (size_t)M + 1) / 2 + 3;
 }

@@ -1,5 +1,6 @@
+"""Fast mode against reference-order mode (bit-identical to the reference) on every trajectory of C4 at a perturbed point."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fast_racing_b200 import api, synth
 B = 1024
