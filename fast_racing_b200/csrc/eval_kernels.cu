@@ -64,7 +64,8 @@ __device__ __forceinline__ double fast_rcp3(double x) {
 }
 
 // CTA-wide barrier usable from warp-specialised branches (both warps of the 64-thread CTA arrive at barrier 1).
-__device__ __forceinline__ void cta_bar64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+// (barrier.sync, not bar.sync = barrier.sync.aligned: warp 0 reaches it from lanes that have not reconverged)
+__device__ __forceinline__ void cta_bar64() { asm volatile("barrier.sync 1, 64;" ::: "memory"); }
 
 // Phase clocks (debug builds only: FRX_NVCC_EXTRA=-DFRX_PHASE_CLK): lane 0 of each warp of one CTA records clock64()
 // at phase boundaries; scripts/phase_clocks.py prints the differences.  Slot = kernel*32 + warp*16 + mark.

@@ -287,7 +287,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
         if (tid == 0) {
 #pragma unroll
             for (int i = 0; i < UPD_NST_MAX; i++)
-                if (i < NST) mbar_init(full_bar + i, 1), mbar_init(empty_bar + i, UPD_THREADS / 32);
+                if (i < NST) mbar_init(full_bar + i, 1), mbar_init(empty_bar + i, UPD_THREADS);
         }
         for (int i = tid; i < n; i += UPD_THREADS) vec[i] = yn[i], vec[nv + i] = sn[i], vec[2 * nv + i] = g[i];
         // rows `end` of S and Y were stored by this CTA a moment ago (generic proxy); the bulk copies below read them through
@@ -322,7 +322,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 }
             }
         };
-        // Ring protocol: a stage is released by its eight consumer warps through an "empty" mbarrier (one arrival per warp), and
+        // Ring protocol: a stage is released by its consumers through an "empty" mbarrier (one arrival per thread), and
         // lane 0 of warp 0 refills the stage of chunk q - 1 at the top of iteration q — the warps meet at a CTA barrier only
         // where their partial tiles are combined (once per row block and array), not once per chunk.
         double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator pairs: the DMMAs of a tile alternate between them
@@ -352,8 +352,7 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 dmma_884(c0, c1, av, bv);
                 dmma_884(e0, e1, aw, bw);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + stg);  // this warp is done with the stage
+            mbar_arrive(empty_bar + stg);  // this thread is done with the stage (its own arrival orders its own reads)
             if (ct == hs.CT - 1) {
                 double* pw = part + (size_t)(ga & 1) * (8 * 8 * 3) + warp * (8 * 3);
                 if (rok) {
@@ -365,10 +364,12 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 flush(ga);
             }
         }
-        // the first chunks of pass 2 are requested now and arrive under the two recursions (the group barrier above was passed
-        // by every warp after its last tile: all stages are free)
-        if (tid == 0)
+        // the first chunks of pass 2 are requested now and arrive under the two recursions (every stage has been released: the
+        // waits below return at once, the group barrier above was passed by every thread after its last tile)
+        if (tid == 0) {
+            for (int q = max(0, Q1 - NST); q < Q1; q++) mbar_wait(empty_bar + q % NST, (q / NST) & 1);
             for (int j = 0; j < min(NST, Q2); j++) hist_issue_rows(hs, Q1 + j, Q2 - 1 - j);
+        }
     } else
     // ---- pass 1 ----
     for (int l = warp; l < bound; l += UPD_THREADS / 32) {
@@ -470,12 +471,11 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
         double acc[UPD_COLS];
 #pragma unroll
         for (int e = 0; e < UPD_COLS; e++) acc[e] = (tid + e * UPD_THREADS < n) ? dg * vec[2 * nv + tid + e * UPD_THREADS] : 0.0;
+        // (pass 2 has no cross-warp exchange, so its ring could run on the empty mbarriers alone, and did: same speed, but
+        // compute-sanitizer's racecheck does not follow mbarrier ordering between reader threads and the refilling copy and
+        // reports the refill as a hazard; a CTA barrier per chunk costs nothing measurable here and keeps the tool quiet)
         for (int j = 0; j < Q2; j++) {
             const int seq = Q1 + j, q = Q2 - 1 - j, stg = seq % NST;
-            if (tid == 0 && j >= 1 && j - 1 + NST < Q2) {
-                mbar_wait(empty_bar + (seq - 1) % NST, ((seq - 1) / NST) & 1);
-                hist_issue_rows(hs, seq - 1 + NST, q + 1 - NST);
-            }
             mbar_wait(full_bar + stg, (seq / NST) & 1);
             const int r0 = (q >> 1) * hs.R2, rows = min(hs.R2, bound - r0);
             const double* chunk = dyn + (size_t)stg * hs.ch;
@@ -487,8 +487,8 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
                 for (int e = 0; e < UPD_COLS; e++)
                     if (tid + e * UPD_THREADS < n) acc[e] += co * chunk[(size_t)r * ld + tid + e * UPD_THREADS];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar + stg);
+            __syncthreads();  // every thread is done with this stage: refill it
+            if (tid == 0 && j + NST < Q2) hist_issue_rows(hs, seq + NST, q - NST);
         }
 #pragma unroll
         for (int e = 0; e < UPD_COLS; e++)
