@@ -203,6 +203,26 @@ static int cuda_fail(cudaError_t e, const char* what) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
+// Every entry point runs on its handle's device and gives the caller's current device back on return (a planner with
+// several GPUs, or torch in the same process, keeps its own current device).
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;  // nothing to restore
+    }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define ON_DEVICE(dev)             \
+    DeviceScope device_scope_(dev); \
+    if (!device_scope_.ok) return cuda_fail(cudaErrorInvalidDevice, "cudaSetDevice")
+
 // ---- batched V-polytope extraction on the device ----------------------------------------------------
 // For every problem that does not bring its own V-polytopes: all 2 n_poly - 1 polytopes (P_0, P_0^P_1, P_1, ...,
 // se3gcopter_cpu.hpp:1031-1074) of all problems go through ONE launch of enumerate_vertices_kernel; the result is handed to
@@ -336,7 +356,8 @@ int frx_cloud_create(const double* obs, int n_obs, int device_ordinal, frx_cloud
         }
     } else
         c->device = device_ordinal;
-    if (cudaSetDevice(c->device) != cudaSuccess || cudaMalloc(&c->obs, sizeof(double) * 3 * (size_t)n_obs) != cudaSuccess ||
+    DeviceScope device_scope_(c->device);
+    if (!device_scope_.ok || cudaMalloc(&c->obs, sizeof(double) * 3 * (size_t)n_obs) != cudaSuccess ||
         cudaMemcpy(c->obs, obs, sizeof(double) * 3 * (size_t)n_obs, cudaMemcpyHostToDevice) != cudaSuccess) {
         if (c->obs) cudaFree(c->obs);
         delete c;
@@ -347,13 +368,13 @@ int frx_cloud_create(const double* obs, int n_obs, int device_ordinal, frx_cloud
 }
 void frx_cloud_destroy(frx_cloud* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceScope device_scope_(c->device);
     if (c->obs) cudaFree(c->obs);
     delete c;
 }
 int frx_cloud_dilate_batch(frx_cloud* c, const double* segments, int n_seg, const double* bbox, int* face_cnt, double* faces, double* ellipsoids) {
     if (!c || !segments || n_seg < 1 || !bbox || !face_cnt || !faces) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     double *d_seg = nullptr, *d_faces = nullptr, *d_ell = nullptr;
     int *d_idx = nullptr, *d_cnt = nullptr;
     unsigned char *d_alive = nullptr, *d_in0 = nullptr;
@@ -453,7 +474,7 @@ const char* frx_strerror(int s) {
 
 void frx_batch_destroy(frx_batch* b) {
     if (!b) return;
-    cudaSetDevice(b->device);
+    DeviceScope device_scope_(b->device);
     if (b->solver) frx_fast::solver_destroy(b->solver);
     if (b->solver_x) frx_exact::solver_destroy(b->solver_x);
     for (auto& d : b->bufs) d.release();
@@ -487,7 +508,8 @@ int frx_batch_create(const frx_problem* problems, int count, int device_ordinal,
         }
     } else
         b->device = device_ordinal;
-    if (cudaSetDevice(b->device) != cudaSuccess) {
+    DeviceScope device_scope_(b->device);
+    if (!device_scope_.ok) {
         delete b;
         return FRX_ERR_CUDA;
     }
@@ -739,7 +761,7 @@ int frx_batch_initial_guess(frx_batch* b, double* x_host) {
     }
     // setInitial + backwardT on the host (sequential in the polytopes, a few hundred flops per trajectory), then the M - 1
     // waypoint solves of backwardP per trajectory on the device, one thread each
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const int TP = b->bv.total_pieces;
     std::vector<double> targets(3 * (size_t)TP, 0.0);
     {
@@ -789,7 +811,7 @@ void* frx_batch_stream(frx_batch* b) { return b ? (void*)b->stream : nullptr; }
 
 int frx_batch_eval_device(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream) {
     if (!b || !x_dev || !cost_dev || !grad_dev) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     cudaStream_t st = (cudaStream_t)stream;
     CK(b->eval_on(x_dev, cost_dev, grad_dev, st));
     return FRX_OK;
@@ -797,7 +819,7 @@ int frx_batch_eval_device(frx_batch* b, const double* x_dev, double* cost_dev, d
 
 int frx_batch_eval(frx_batch* b, const double* x_host, double* cost_host, double* grad_host) {
     if (!b || !x_host || !cost_host || !grad_host) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     const size_t nx = sizeof(double) * (size_t)b->bv.total_x;
     if (x_host != b->x_pin) std::memcpy(b->x_pin, x_host, nx);  // staging only for foreign (pageable) buffers
     CK(cudaEventRecord(b->ev0, b->stream));
@@ -858,7 +880,7 @@ double frx_batch_last_ms(const frx_batch* b) { return b ? b->last_ms : -1.0; }
 int frx_batch_profile_eval(frx_batch* b, const double* x_dev, double* cost_dev, double* grad_dev, void* stream, int reps,
                            double* ms_out) {
     if (!b || !x_dev || !cost_dev || !grad_dev || !ms_out || reps < 1) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     if (b->exact)
         CK(frx_exact::profile_eval(b->bv, b->pl, b->fwd_smem_x, b->bwd_smem_x, x_dev, cost_dev, grad_dev, (cudaStream_t)stream, reps, ms_out));
     else
@@ -910,7 +932,7 @@ int frx_batch_argmin_allgather(frx_batch* b, void* nccl_comm, int n_ranks, long 
             return FRX_ERR_CUDA;
         }
     }
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     int idx = -1;
     double val = 0.0;
     int s = frx_batch_argmin(b, &idx, &val);
@@ -950,7 +972,7 @@ int frx_batch_set_reference_order(frx_batch* b, int on) {
 int frx_batch_debug_fetch(frx_batch* b, double* T, double* q, double* c, double* lambda, double* pen, double* energy,
                           double* gdT) {
     if (!b) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     CK(cudaStreamSynchronize(b->stream));
     const size_t TP = b->bv.total_pieces;
     if (T) CK(cudaMemcpy(T, b->bv.T, sizeof(double) * TP, cudaMemcpyDeviceToHost));
@@ -1016,7 +1038,7 @@ int frx_host_vpolys(const frx_problem* p, int* vert_off, double* verts) {
 int frx_batch_optimize(frx_batch* b, double rel_tol, double* durations, double* coeffs, double* jerk_cost,
                        double* final_cost, int* lbfgs_status, int* iterations, int* evaluations, double* x_final) {
     if (!b) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     // starting point: setInitial + backwardT/P on the host, one H2D copy
     std::vector<double> x0((size_t)b->bv.total_x);
     int s = frx_batch_initial_guess(b, x0.data());
@@ -1120,7 +1142,7 @@ int frx_batch_solver_direction_check(const frx_batch* b, double* max_rel) {
 
 int frx_batch_argmin(frx_batch* b, int* best_traj, double* best_cost) {
     if (!b || !b->have_final) return FRX_ERR_INVALID_ARG;
-    CK(cudaSetDevice(b->device));
+    ON_DEVICE(b->device);
     int idx = -1;
     double val = 0.0;
     int s = b->last_solver_exact ? frx_exact::solver_argmin(b->solver_x, b->final_cost_dev, b->bv.B, b->stream, &idx, &val)

@@ -18,6 +18,7 @@
  *  - There is NO CPU fallback: if no CUDA device is usable every compute entry point returns
  *    FRX_ERR_CUDA.
  *  - A frx_batch is not thread-safe; distinct batches are independent (each owns its stream).
+ *  - Every entry point runs on its handle's device and leaves the caller's current device as it found it.
  */
 #ifndef FRX_H_
 #define FRX_H_

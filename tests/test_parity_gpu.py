@@ -144,6 +144,27 @@ def test_batches_of_different_shapes_coexist(oracle_mod):
     bb.close()
 
 
+def test_entry_points_leave_the_callers_current_device_alone():
+    """Every C-ABI entry point runs on its handle's device and restores the caller's current device (a planner with several
+    GPUs, or torch in the same process, keeps its own).  Needs two GPUs to be observable."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rt = C.CDLL("libcudart.so.12")
+    cur = C.c_int(-1)
+    rt.cudaSetDevice(0)
+    b = api.Batch(synth.make_batch(420, 2, 4, 8, 8), device=1)
+    rt.cudaGetDevice(C.byref(cur))
+    assert cur.value == 0
+    c, g = b.eval(b.initial_guess())
+    r = b.optimize(1e-3)
+    rt.cudaGetDevice(C.byref(cur))
+    assert cur.value == 0 and np.isfinite(c).all() and np.isfinite(r["final_cost"]).all()
+    b.close()
+    rt.cudaGetDevice(C.byref(cur))
+    assert cur.value == 0
+
+
 def test_solvers_of_different_shapes_coexist():
     """The update kernel's dynamic shared-memory limit (ring of the streamed history) is per function and process-global too:
     a solver created later for SMALLER trajectories must not lower it under a live larger one.  Solves are deterministic, so
