@@ -103,9 +103,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 // coefficient space of the basis {s_l, y_l, g} ("vector-free" L-BFGS): the sequential recursion
 // (2*bound dependent dot products of length n, each a CTA-wide reduction) becomes
 //   pass 1  one streaming pass over the history: the Gram entries that involve the NEW pair and the
-//           new gradient (5 independent dot products per history slot, one warp per slot),
-//   loops   the two recursions on bound x bound Gram matrices, done by one warp in registers,
-//   pass 2  one streaming pass: d = dg*g + sum_l a_l s_l + b_l y_l.
+//           new gradient (row . (y_new, s_new, g) for every row of S and Y: streamed through a TMA-fed
+//           shared-memory ring and contracted on the fp64 tensor cores, see direction_vector_free;
+//           plain loads, one warp per history slot, when the ring does not apply),
+//   loops   the two recursions on bound x bound Gram matrices (blocked_recursion),
+//   pass 2  one streaming pass: d = dg*g + sum_l a_l s_l + b_l y_l (same ring, whole rows).
 // Same mathematics as the reference's recursion; the summation order differs (stated tolerance).
 // Gram matrices per trajectory: SY[i][j] = s_i.y_j, SYT = SY^T, YY[i][j] = y_i.y_j (m x m each).
 // Requires m <= 128 and UPD_THREADS == 256.

@@ -7,8 +7,9 @@
 //   (2) lbfgs_update_kernel: one CTA per trajectory consumes (f, g): directional derivative,
 //       More-Thuente / backtracking transition, and — when a line search finishes — convergence
 //       tests, (s, y) history update, two-loop recursion and the first trial point of the next
-//       iteration.  Finished trajectories are masked out of all four kernels.
-// The host only polls a device counter of unfinished trajectories every few ticks.
+//       iteration.  The four kernels run over solver slots (SolverView::slot_list): a finished trajectory hands its
+//       slot to the next one of the batch, or leaves it empty.
+// The host only polls a device counter of unfinished trajectories every few ticks; a poll group of ticks is one CUDA graph.
 #pragma once
 #include <cuda_runtime.h>
 
