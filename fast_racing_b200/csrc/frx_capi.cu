@@ -148,10 +148,10 @@ static bool node_cpuset(int node, cpu_set_t* set) {
     FILE* f = std::fopen(path, "r");
     if (!f) return false;
     CPU_ZERO(set);
-    int a = 0, b2 = 0, n = 0;
+    int a = 0, b2 = 0;
     bool any = false;
     char sep = 0;
-    while ((n = std::fscanf(f, "%d", &a)) == 1) {
+    while (std::fscanf(f, "%d", &a) == 1) {
         b2 = a;
         if (std::fscanf(f, "%c", &sep) == 1 && sep == '-') {
             if (std::fscanf(f, "%d", &b2) != 1) break;
