@@ -899,6 +899,14 @@ int frx_debug_cta_spans(unsigned long long* out) {
     CK(frx_fast::fetch_cta_spans(out));
     return FRX_OK;
 }
+// Host-side view of the update kernel's shared-memory ring (no device needed): out[8] = {stages, doubles per stage, dynamic smem
+// bytes, tile width, column tiles, rows per pass-2 chunk, streamed (0/1), fixed doubles} for a trajectory of n variables in a
+// batch of `batch` trajectories whose largest has max_n.  tests/test_host_cpu.py checks the invariants the bulk copies rely on.
+int frx_debug_update_ring(int max_n, int n, int batch, int* out8) {
+    if (!out8 || max_n < 1 || n < 1 || n > max_n || batch < 1) return FRX_ERR_INVALID_ARG;
+    frx_fast::debug_update_ring(max_n, n, batch, out8);
+    return FRX_OK;
+}
 int frx_debug_update_clocks(long long* out16, int reset) {
     if (!out16) return FRX_ERR_INVALID_ARG;
     CK(frx_fast::fetch_update_clocks(out16, reset));

@@ -222,6 +222,23 @@ __device__ __forceinline__ void blocked_recursion(const double* __restrict__ Mx,
 #define UPD_NST_MAX 8  // ring stages: sv.upd_nst <= UPD_NST_MAX
 #define UPD_PART (2 * 8 * 8 * 3)  // doubles: the eight per-warp partial 8 x 3 tiles of two row blocks
 #define UPD_COLS 8                // columns per thread in pass 2: n <= UPD_COLS * UPD_THREADS
+// Geometry of one trajectory's chunks inside a ring whose stages hold `ch` doubles: tile width W (a multiple of 32, or the
+// whole padded row) and column tiles per row for pass 1, rows per chunk for pass 2; ok = the streamed passes apply.  Shared by
+// the kernel and the host (frx_debug_update_ring -> tests/test_host_cpu.py checks the invariants the bulk copies rely on).
+struct RingGeom {
+    int W, CT, R2;
+    bool ok;
+};
+__host__ __device__ inline RingGeom ring_geometry(int n, int ld, int m, int ch) {
+    RingGeom g;
+    const int wmax = (ch / 8 - 4) & ~31;  // widest tile the stage holds, multiple of 32
+    g.W = (ld <= wmax || wmax < 32) ? ld : wmax;
+    g.CT = (ld + g.W - 1) / g.W;
+    const int r = ch / ld;
+    g.R2 = r < 1 ? 1 : (r > m ? m : r);
+    g.ok = ld <= ch && 8 * (g.W + 4) <= ch && (m & 7) == 0 && n <= UPD_COLS * UPD_THREADS;
+    return g;
+}
 struct HistStream {
     double* ring;              // nst * ch doubles
     unsigned long long* full;  // nst mbarriers
@@ -273,13 +290,9 @@ __device__ void direction_vector_free(const SolverView& sv, int b, int n, int ld
     HistStream hs;
     hs.ring = dyn, hs.full = full_bar, hs.S = S, hs.Y = Y, hs.n = n, hs.ld = ld, hs.m = m, hs.ch = sv.upd_ch, hs.nst = sv.upd_nst;
     const int NST = sv.upd_nst;
-    {
-        const int wmax = (sv.upd_ch / 8 - 4) & ~31;  // widest tile the stage holds, multiple of 32
-        hs.W = (ld <= wmax || wmax < 32) ? ld : wmax;
-        hs.CT = (ld + hs.W - 1) / hs.W;
-        hs.R2 = max(1, min(m, sv.upd_ch / ld));
-    }
-    const bool streamed = dyn != nullptr && ld <= sv.upd_ch && 8 * (hs.W + 4) <= sv.upd_ch && (m & 7) == 0 && n <= UPD_COLS * UPD_THREADS;
+    const RingGeom geo = ring_geometry(n, ld, m, sv.upd_ch > 0 ? sv.upd_ch : 2);
+    hs.W = geo.W, hs.CT = geo.CT, hs.R2 = geo.R2;
+    const bool streamed = dyn != nullptr && geo.ok;
     const int Q1 = 2 * ((bound + 7) >> 3) * hs.CT;       // chunks of pass 1
     const int Q2 = 2 * ((bound + hs.R2 - 1) / hs.R2);    // chunks of pass 2
     const int nv = (n + 1) & ~1;
@@ -856,6 +869,42 @@ static cudaError_t dalloc(SolverState* s, size_t n, T** out) {
     return cudaMemset(p, 0, sizeof(T) * (n ? n : 1));
 }
 
+// Ring of the streamed direction update for a batch whose largest trajectory has max_n variables: stages, doubles per stage,
+// dynamic shared memory (0: plain loads).  Few trajectories (at most two per SM anyway): one CTA per SM with a deep ring streams
+// fastest.  Many: two CTAs per SM, so that one streams while the other runs its recursions (profiles/r02_update_kernel.txt has
+// the sweep).  budget_kb / nst > 0 override the first choice (experiments).
+void update_ring_config(int max_n, int B, int budget_kb, int nst, int* out_nst, int* out_ch, int* out_smem) {
+    *out_nst = 0, *out_ch = 0, *out_smem = 0;
+    if (max_n < 1 || max_n > UPD_COLS * UPD_THREADS) return;
+    const int ldm = (max_n + 1) & ~1, fixed = UPD_PART + 3 * ldm;
+    struct Cfg {
+        int budget_kb, nst;
+    };
+    const bool few = B <= 2 * 148;
+    Cfg cfgs[3] = {few ? Cfg{200, 4} : Cfg{96, 3}, Cfg{200, 4}, Cfg{200, 2}};
+    if (budget_kb > 0) cfgs[0].budget_kb = budget_kb;
+    if (nst > 0) cfgs[0].nst = nst;
+    for (const Cfg& c : cfgs) {
+        const int ch = ((c.budget_kb * 1024 / 8 - fixed) / c.nst) & ~1;
+        if (ch >= ldm && ch >= 8 * (32 + 4)) {
+            *out_ch = std::min(ch, std::max(8 * (((ldm + 31) & ~31) + 4), 2 * ldm));  // no more than one row block x whole rows
+            *out_nst = c.nst;
+            *out_smem = (int)(sizeof(double) * ((size_t)c.nst * *out_ch + fixed));
+            return;
+        }
+    }
+}
+// Host-side view of the ring for tests: out[8] = {stages, doubles per stage, dynamic smem bytes, W, CT, R2, streamed, fixed doubles}
+// for a trajectory of n variables in a batch of `batch` whose largest has max_n.
+void debug_update_ring(int max_n, int n, int batch, int* out) {
+    int nst = 0, ch = 0, smem = 0;
+    update_ring_config(max_n, batch, 0, 0, &nst, &ch, &smem);
+    const int ld = (n + 1) & ~1;
+    const RingGeom g = ring_geometry(n, ld, 128, ch > 0 ? ch : 2);
+    out[0] = nst, out[1] = ch, out[2] = smem, out[3] = g.W, out[4] = g.CT, out[5] = g.R2, out[6] = (smem > 0 && g.ok) ? 1 : 0;
+    out[7] = UPD_PART + 3 * ((max_n + 1) & ~1);
+}
+
 int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverState** out) {
     SolverState* s = new SolverState();
     s->x_off = x_off;
@@ -888,21 +937,10 @@ int solver_create(const BatchView& bv, const std::vector<int>& x_off, SolverStat
         if (sv.vector_free && !(e && e[0] == '0') && max_n <= UPD_COLS * UPD_THREADS) {
             // Few trajectories (at most two per SM anyway): one CTA per SM with a deep ring streams fastest.  Many: two CTAs per
             // SM, so that one streams while the other runs its recursions.  (profiles/r02_update_kernel.txt has the sweep.)
-            const int ldm = (max_n + 1) & ~1, fixed = UPD_PART + 3 * ldm;
-            struct Cfg { int budget_kb, nst; };
-            const bool few = bv.B <= 2 * 148;
-            Cfg cfgs[3] = {few ? Cfg{200, 4} : Cfg{96, 3}, Cfg{200, 4}, Cfg{200, 2}};
-            if (const char* eb = getenv("FRX_UPD_BUDGET_KB")) cfgs[0].budget_kb = atoi(eb);  // experiments
-            if (const char* en = getenv("FRX_UPD_NST")) cfgs[0].nst = std::max(2, std::min(UPD_NST_MAX, atoi(en)));
-            for (const Cfg& c : cfgs) {
-                const int ch = ((c.budget_kb * 1024 / 8 - fixed) / c.nst) & ~1;
-                if (ch >= ldm && ch >= 8 * (32 + 4)) {
-                    sv.upd_ch = std::min(ch, std::max(8 * (((ldm + 31) & ~31) + 4), 2 * ldm));  // no more than one row block x whole rows
-                    sv.upd_nst = c.nst;
-                    sv.upd_smem = (int)(sizeof(double) * ((size_t)c.nst * sv.upd_ch + fixed));
-                    break;
-                }
-            }
+            int budget_kb = 0, nst = 0;
+            if (const char* eb = getenv("FRX_UPD_BUDGET_KB")) budget_kb = atoi(eb);  // experiments
+            if (const char* en = getenv("FRX_UPD_NST")) nst = std::max(2, std::min(UPD_NST_MAX, atoi(en)));
+            update_ring_config(max_n, bv.B, budget_kb, nst, &sv.upd_nst, &sv.upd_ch, &sv.upd_smem);
             if (sv.upd_smem) {
                 // the attribute is per function and per device, shared by every solver of the process: only ever raise it
                 // (a second, smaller batch must not lower the limit under a larger one that is still alive)

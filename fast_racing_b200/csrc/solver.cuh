@@ -87,6 +87,7 @@ struct SolverIO {
     int solver_argmin(SolverState* s, const double* cost_dev, int B, cudaStream_t st, int* idx, double* val);               \
     int solver_ticks(SolverState* s);                                                                                       \
     cudaError_t fetch_update_clocks(long long* out16, int reset);                                                           \
+    void debug_update_ring(int max_n, int n, int batch, int* out8);                                                         \
     /* sampled lbfgs_update_kernel launches of the last run: device ms, algorithmic bytes streamed, number of samples */   \
     int solver_update_stats(SolverState* s, double* ms, double* bytes, int* samples);                                       \
     int solver_direction_check(SolverState* s, double* max_rel);                                                            \

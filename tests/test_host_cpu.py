@@ -143,3 +143,43 @@ def test_argmin_gather_world_size_2_gloo():
     assert (res[0][1], res[0][2], res[1][1], res[1][2]) == (0, 6, 6, 11)  # block partition
     for r in res:
         assert r[3] == 1.5 and r[4] == 5  # ties -> lowest global index, same answer on every rank
+
+
+def test_update_kernel_ring_geometry_invariants():
+    """The streamed L-BFGS direction update (csrc/solver.cu) copies the history with 1-D bulk copies, which need 16-byte aligned
+    addresses and sizes and must fit their stage.  The ring configuration (host) and the per-trajectory chunk geometry (the SAME
+    __host__ __device__ function the kernel calls) are checked here for every largest-trajectory size the streamed path takes
+    (1..2048 variables), small and large batches, and ragged members of a batch: sizes, alignment, coverage, shared-memory budget."""
+    lib = api.load_library()
+    lib.frx_debug_update_ring.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.frx_debug_update_ring.restype = C.c_int
+    out = (C.c_int * 8)()
+    M_HIST, STATIC_SMEM, SM_SMEM, RESERVED = 128, 14592, 233472, 1024  # history depth; update kernel's static smem; per-SM; per-CTA
+    streamed_sizes = 0
+    for batch in (1, 296, 297, 4096):
+        for max_n in list(range(1, 300)) + list(range(300, 2049, 7)) + [1183, 1184, 2047, 2048]:
+            members = sorted(v for v in {max_n, 1, 2, 3, max(1, max_n // 2), max(1, max_n - 1)} if v <= max_n)
+            for n in members:
+                assert lib.frx_debug_update_ring(max_n, n, batch, out) == 0
+                nst, ch, smem, W, CT, R2, streamed, fixed = list(out)
+                assert streamed == 1, (batch, max_n, n)  # every size up to 2048 takes the streamed path
+                streamed_sizes += 1
+                ld = (n + 1) & ~1
+                assert 2 <= nst <= 8 and ch % 2 == 0 and smem == 8 * (nst * ch + fixed)
+                assert smem + STATIC_SMEM <= 227 * 1024  # opt-in limit per CTA
+                if batch > 296:  # many trajectories: two CTAs per SM must fit whenever the small configuration was taken
+                    if nst == 3:
+                        assert 2 * (smem + STATIC_SMEM + RESERVED) <= SM_SMEM, (max_n, smem)
+                # pass 1: tiles of 8 rows x W columns, row stride W + 4 doubles in the stage
+                assert W % 2 == 0 and (W == ld or W % 32 == 0) and 8 * (W + 4) <= ch
+                assert (CT - 1) * W < ld <= CT * W
+                for ct in range(CT):
+                    wt = min(W, ld - ct * W)
+                    assert wt > 0 and wt % 2 == 0 and (ct * W) % 2 == 0  # 16-byte aligned source, 16-byte multiple
+                # pass 2: R2 whole rows per chunk
+                assert 1 <= R2 <= M_HIST and R2 * ld <= ch
+                # the three vectors + partial tiles behind the ring
+                assert fixed >= 2 * 8 * 8 * 3 + 3 * ld
+    assert streamed_sizes > 5000
+    # beyond 8 columns per thread the plain-load path takes over
+    assert lib.frx_debug_update_ring(2049, 2049, 1024, out) == 0 and out[2] == 0 and out[6] == 0
